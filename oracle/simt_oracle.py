@@ -1,0 +1,307 @@
+"""CPU oracle for the SimT per-pixel head and the integer eval histograms.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``simt_b200/`` imports it and
+the product path raises if the CUDA library is missing.
+
+It restates, op for op, the reference's algorithm for the hot path using the
+same third-party primitives the reference calls (PyTorch CPU ops, numpy
+bincount).  The arithmetic itself lives in un-vendored third-party code
+(PyTorch -- the reference only says "Pytorch 1.3 & 1.7 are ok", README.md:18-21;
+here torch 2.11.0, numpy 2.3.5), so what is restated is the reference's
+*composition* of those primitives; each function cites the reference lines it
+follows (paths relative to the reference root).
+
+Parity pinning: the reference ships NO tests, golden vectors or fixtures for
+this path.  The oracle is therefore pinned against outputs of
+the reference itself: ``oracle/make_golden.py`` imports the unmodified
+reference modules (``utils/loss.py``, ``model/deeplab_multi.py``,
+``tools/compute_iou.py``) in the build container, runs them on seeded
+synthetic inputs and commits inputs + outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this file against those vectors
+bit-for-bit (fp32 and fp64) on CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IGNORE_LABEL = 255
+
+
+# --------------------------------------------------------------------------
+# a1: bilinear resize, align_corners=True
+# --------------------------------------------------------------------------
+def upsample_bilinear_ac(x: torch.Tensor, size) -> torch.Tensor:
+    """``nn.Upsample(size=(H, W), mode='bilinear', align_corners=True)``.
+
+    Reference: tools/trainV2_simt.py:301 (``interp_target``), applied at
+    :371-372 and again (identity size) at :402,405.  ``nn.Upsample.forward``
+    is ``F.interpolate`` with the same arguments.
+    """
+    return F.interpolate(x, size=tuple(size), mode="bilinear", align_corners=True)
+
+
+# --------------------------------------------------------------------------
+# a4: CrossEntropy2d
+# --------------------------------------------------------------------------
+def cross_entropy_2d(predict: torch.Tensor, target: torch.Tensor, *, is_softmax: bool,
+                     ignore_label: int = IGNORE_LABEL, weight=None) -> torch.Tensor:
+    """Masked mean CE / NLL over valid pixels.
+
+    Reference: utils/loss.py:14-40.  Mask ``(t >= 0) & (t != ignore)`` (:29),
+    labels gathered by the mask (:30), NCHW -> NHWC contiguous copy (:33),
+    rows gathered by the same mask (:34), then ``F.cross_entropy`` on logits
+    (:36) or ``log`` + ``F.nll_loss`` on probabilities (:38-39), mean
+    reduction.  The early return at :31-32 is unreachable for a 3-d target
+    (an empty selection is still 1-d) and is therefore not restated; an
+    all-ignored target gives NaN exactly as the reference does.
+    """
+    assert not target.requires_grad
+    assert predict.dim() == 4 and target.dim() == 3
+    assert predict.size(0) == target.size(0)
+    assert predict.size(2) == target.size(1)
+    assert predict.size(3) == target.size(2)
+    n, c, h, w = predict.size()
+    valid = (target >= 0) * (target != ignore_label)
+    picked = target[valid]
+    rows = predict.transpose(1, 2).transpose(2, 3).contiguous()
+    rows = rows[valid.view(n, h, w, 1).repeat(1, 1, 1, c)].view(-1, c)
+    if is_softmax:
+        return F.cross_entropy(rows, picked, weight=weight, reduction="mean")
+    return F.nll_loss(torch.log(rows), picked, weight=weight, reduction="mean")
+
+
+# --------------------------------------------------------------------------
+# a1-a4 composed: the T-corrected head exactly as the training loop runs it
+# --------------------------------------------------------------------------
+def simt_head_loss(logits_lo: torch.Tensor, T: torch.Tensor, labels: torch.Tensor, out_size,
+                   ignore_label: int = IGNORE_LABEL) -> torch.Tensor:
+    """loss_y = Tseg_loss(mm(softmax(interp(interp(pred))), T), label).
+
+    Reference: tools/trainV2_simt.py:371-372 (first upsample), :402-403 /
+    :405-406 (second, same-size upsample; channel softmax; NHWC flatten;
+    ``torch.mm`` with T [CK, C]; reshape back to NCHW), :408-409
+    (``CrossEntropy2d(is_softmax=False)``, built at :304).
+    """
+    B, CK = logits_lo.shape[:2]
+    H, W = out_size
+    C = T.shape[1]
+    up = upsample_bilinear_ac(logits_lo, (H, W))                       # :371-372
+    p = torch.softmax(upsample_bilinear_ac(up, (H, W)), dim=1)         # :402
+    p = p.permute(0, 2, 3, 1).contiguous().view(-1, CK)
+    q = torch.mm(p, T).view(B, H, W, C).permute(0, 3, 1, 2)            # :403
+    return cross_entropy_2d(q, labels, is_softmax=False, ignore_label=ignore_label)  # :408
+
+
+def plain_ce_loss(logits_lo: torch.Tensor, labels: torch.Tensor, out_size,
+                  ignore_label: int = IGNORE_LABEL) -> torch.Tensor:
+    """``seg_loss(interp(pred), label)`` with ``CrossEntropyLoss(ignore_index=255)``.
+
+    Reference: tools/trainV2_simt.py:303,394-395 and tools/trainV1_warmup.py:203,
+    218-224 (the T = identity special case of the head).
+    """
+    up = upsample_bilinear_ac(logits_lo, out_size)
+    return F.cross_entropy(up, labels, ignore_index=ignore_label)
+
+
+def simt_head_fwd_bwd(logits_lo, T, labels, out_size, dtype=torch.float32, ignore_label=IGNORE_LABEL):
+    """Run the head forward + autograd backward on CPU; returns (loss, dLogits, dT)."""
+    lg = logits_lo.detach().to(dtype).clone().requires_grad_(True)
+    Tt = T.detach().to(dtype).clone().requires_grad_(True)
+    loss = simt_head_loss(lg, Tt, labels.long(), out_size, ignore_label)
+    loss.backward()                                                    # :428
+    return loss.detach(), lg.grad.detach(), Tt.grad.detach()
+
+
+# --------------------------------------------------------------------------
+# a6 / a7: the T layer and the convex-hull weight layer (forward maths only)
+# --------------------------------------------------------------------------
+def sig_ntm_forward(NTM: torch.Tensor, class_dist: torch.Tensor, num_classes: int,
+                    open_classes: int = 0) -> torch.Tensor:
+    """T = L1-row-normalise(sigmoid(NTM) * tile(ClassDist) + [I_C; 0]).
+
+    Reference: model/deeplab_multi.py:254-257 (buffers), :259-263 (forward).
+    ``class_dist`` is the float64[19] npy cast through ``torch.FloatTensor``.
+    """
+    ck = num_classes + open_classes
+    ident = torch.cat([torch.eye(num_classes, num_classes), torch.zeros(open_classes, num_classes)], 0)
+    dist = torch.as_tensor(np.tile(np.asarray(class_dist), (ck, 1))).to(torch.float32)
+    T = torch.sigmoid(NTM)
+    T = T.mul(dist.to(NTM.dtype)) + ident.to(NTM.dtype)
+    return F.normalize(T, p=1, dim=1)
+
+
+def sig_w_forward(weight: torch.Tensor) -> torch.Tensor:
+    """W = softmax(weight with diag forced to -1e4, dim=1) - I.
+
+    Reference: model/deeplab_multi.py:277-286.  Mutates ``weight`` in place
+    under no_grad like the reference does (:279-281).
+    """
+    n = weight.shape[0]
+    idx = np.diag_indices(n)
+    with torch.no_grad():
+        weight[idx[0], idx[1]] = -10000.0 * torch.ones(n, dtype=weight.dtype)
+    w = torch.softmax(weight, dim=1)
+    return (torch.zeros(n, n, dtype=weight.dtype) - torch.eye(n, dtype=weight.dtype)) + w
+
+
+# --------------------------------------------------------------------------
+# a8 / a9 / a10: T regularisers
+# --------------------------------------------------------------------------
+def convex_loss(W_list, T_list) -> torch.Tensor:
+    """NTM_Convex_loss = 0 - sum_heads MSE_sum(W @ T, 0).  trainV2_simt.py:412-415."""
+    mse = torch.nn.MSELoss(reduction="sum")
+    tot = 0.0
+    for W, T in zip(W_list, T_list):
+        tot = tot + mse(W.mm(T), torch.zeros_like(T))
+    return 0.0 - tot
+
+
+def w_fit_loss(W_list, T_list) -> torch.Tensor:
+    """Inner W-optimisation objective, sum_heads ||W T||_F^2.  trainV2_simt.py:336."""
+    return -convex_loss(W_list, T_list)
+
+
+def volume_loss(T_list):
+    """sum_heads log sqrt |det(T^T T)|; inf/nan -> python 0.  trainV2_simt.py:417-421."""
+    tot = None
+    for T in T_list:
+        v = torch.log(torch.sqrt(torch.abs(torch.linalg.det(T.transpose(1, 0).mm(T)))))
+        tot = v if tot is None else tot + v
+    if torch.isinf(tot) or torch.isnan(tot):
+        return 0.0
+    return tot
+
+
+def anchor_stats(pred_up: torch.Tensor):
+    """(Anchor_index[CK], Exist_label) from upsampled logits.  trainV2_simt.py:375-377.
+
+    The reference's ``.view`` on the permuted tensor only works for B = 1;
+    ``reshape`` keeps the B = 1 result and defines B > 1 as "flatten pixels
+    over the batch" (SURVEY section 7).
+    """
+    ck = pred_up.shape[1]
+    flat = pred_up.detach().clone().permute(0, 2, 3, 1).reshape(-1, ck)
+    return torch.argmax(flat, dim=0), torch.unique(torch.argmax(flat, dim=1))
+
+
+def anchor_loss(pred_up_list, T_list, labelC_flat) -> torch.Tensor:
+    """sum_heads MSE_sum(T[Exist], labelC_flat[Anchor_index][Exist]).  :375-384."""
+    mse = torch.nn.MSELoss(reduction="sum")
+    tot = 0.0
+    for pred_up, T in zip(pred_up_list, T_list):
+        a_idx, exist = anchor_stats(pred_up)
+        anchor = labelC_flat[a_idx]
+        tot = tot + mse(T[exist], anchor[exist])
+    return tot
+
+
+def label_c_flat(fixed_logits_lo: torch.Tensor, out_size) -> torch.Tensor:
+    """labelC_flat = interp(softmax(output2)) as [N, C].  trainV2_simt.py:354,357."""
+    c = fixed_logits_lo.shape[1]
+    lc = upsample_bilinear_ac(torch.softmax(fixed_logits_lo.clone(), dim=1), out_size)
+    return lc.permute(0, 2, 3, 1).reshape(-1, c)
+
+
+# --------------------------------------------------------------------------
+# a12 - a16: integer eval histograms (numpy, single-threaded like the reference)
+# --------------------------------------------------------------------------
+def fast_hist(a, b, n):
+    """tools/compute_iou.py:9-11 (dup tools/evaluate_cityscapes.py:81-83)."""
+    k = (a >= 0) & (a < n)
+    return np.bincount(n * a[k].astype(int) + b[k], minlength=n ** 2).reshape(n, n)
+
+
+def fast_hist_rect(a, b, n_rows, n_cols):
+    """tools/compute_ConfusionMatrix.py:54-56 (``fast_hist(a, b, n33, n19)``)."""
+    ka = (a >= 0) & (a < n_rows)
+    return np.bincount(n_cols * a[ka].astype(int) + b[ka], minlength=n_rows * n_cols).reshape(n_rows, n_cols)
+
+
+def class_hist(a, n):
+    """tools/compute_ClassDistribution.py:52-54 (``fast_hist(a, n)``)."""
+    ka = (a >= 0) & (a < n)
+    return np.bincount(a[ka], minlength=n)
+
+
+def per_class_iu(hist):
+    """tools/compute_iou.py:14-15."""
+    return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+
+
+def label_mapping(inp, mapping):
+    """tools/compute_iou.py:18-22: sequential ``out[inp == k] = v`` passes, int64 result."""
+    out = np.copy(inp)
+    for ind in range(len(mapping)):
+        out[inp == mapping[ind][0]] = mapping[ind][1]
+    return np.array(out, dtype=np.int64)
+
+
+def miou_percent(hist) -> float:
+    """``round(np.nanmean(per_class_iu(hist)) * 100, 2)``.  tools/compute_iou.py:55-58."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return round(float(np.nanmean(per_class_iu(hist))) * 100, 2)
+
+
+def class_dist_normalise(counts):
+    """``CM / (sum(CM) + 10e-10)``.  tools/compute_ClassDistribution.py:92."""
+    counts = np.asarray(counts, dtype=np.float64)
+    return counts / (np.sum(counts) + 10e-10)
+
+
+def confusion_row_normalise(cm):
+    """``CM / (rowsum + 10e-6)``.  tools/compute_ConfusionMatrix.py:121."""
+    cm = np.asarray(cm, dtype=np.float64)
+    return cm / (np.sum(cm, axis=1, keepdims=True) + 10e-6)
+
+
+# Cityscapes raw-id -> train-id table, dataset/cityscapes_list/info.json:3-38
+# ("label2train"); classes = 19 (:2).  Data, restated so the GPU box (which has
+# no /root/reference) can build the same 256-entry LUT.
+CITYSCAPES_LABEL2TRAIN = [
+    [0, 255], [1, 255], [2, 255], [3, 255], [4, 255], [5, 255], [6, 255], [7, 0], [8, 1], [9, 255],
+    [10, 255], [11, 2], [12, 3], [13, 4], [14, 255], [15, 255], [16, 255], [17, 5], [18, 255], [19, 6],
+    [20, 7], [21, 8], [22, 9], [23, 10], [24, 11], [25, 12], [26, 13], [27, 14], [28, 15], [29, 255],
+    [30, 255], [31, 16], [32, 17], [33, 18], [-1, 255],
+]
+
+
+# --------------------------------------------------------------------------
+# Seeded synthetic inputs
+# --------------------------------------------------------------------------
+def synth_head_inputs(B, CK, h, w, H, W, *, C=19, seed=1234, coherent=True, ignore_frac=0.10,
+                      class_dist=None, block=32, logit_scale=3.0):
+    """logits ~ 3 N(0,1) f32; labels uniform (u) or block-coherent categorical (r); 10 % -> 255."""
+    g = torch.Generator().manual_seed(seed)
+    logits = logit_scale * torch.randn(B, CK, h, w, generator=g, dtype=torch.float32)
+    rng = np.random.default_rng(seed)
+    if coherent:
+        pdist = np.full(C, 1.0 / C) if class_dist is None else np.asarray(class_dist, dtype=np.float64)
+        pdist = pdist / pdist.sum()
+        bh, bw = -(-H // block), -(-W // block)
+        coarse = rng.choice(C, size=(B, bh, bw), p=pdist)
+        lab = np.repeat(np.repeat(coarse, block, axis=1), block, axis=2)[:, :H, :W]
+    else:
+        lab = rng.integers(0, C, size=(B, H, W))
+    lab = lab.astype(np.uint8)
+    if ignore_frac > 0:
+        lab[rng.random((B, H, W)) < ignore_frac] = IGNORE_LABEL
+    return logits, torch.from_numpy(np.ascontiguousarray(lab))
+
+
+def synth_eval_pair(H, W, *, seed=1234, coherent=True, block=32, n_raw=34, n_pred=19):
+    """(raw-id gt uint8 [H,W] in 0..n_raw-1, pred uint8 [H,W] in 0..n_pred-1)."""
+    rng = np.random.default_rng(seed)
+    if coherent:
+        bh, bw = -(-H // block), -(-W // block)
+        gt = np.repeat(np.repeat(rng.integers(0, n_raw, size=(bh, bw)), block, 0), block, 1)[:H, :W]
+        pr = np.repeat(np.repeat(rng.integers(0, n_pred, size=(bh, bw)), block, 0), block, 1)[:H, :W]
+        flip = rng.random((H, W)) < 0.05
+        pr = np.where(flip, rng.integers(0, n_pred, size=(H, W)), pr)
+    else:
+        gt = rng.integers(0, n_raw, size=(H, W))
+        pr = rng.integers(0, n_pred, size=(H, W))
+    return np.ascontiguousarray(gt.astype(np.uint8)), np.ascontiguousarray(pr.astype(np.uint8))
