@@ -1,0 +1,166 @@
+/*
+ * simt_b200.h -- C ABI of libsimt_b200.so: the B200 (sm_100a) implementation of
+ * SimT's per-pixel training/eval head.
+ *
+ * The reference (CityU-AIM-Group/SimT) has no FFI of its own: the hot path is a
+ * sequence of PyTorch / numpy calls in Python.  Each entry point below replaces
+ * the reference lines cited next to it (paths relative to the reference root);
+ * the Python host mirror in simt_b200/ binds them with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller
+ *     unless the name ends in _host;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *     returns without synchronising; re-entrant across streams as long as each
+ *     in-flight call has its own workspace;
+ *   - return value: 0 on success, a positive cudaError_t from the runtime, or a
+ *     negative SIMT_E* argument-validation code.  No C++ exceptions cross the
+ *     boundary.  simt_b200_strerror() maps any code to text;
+ *   - data-dependent contract violations (a label in [C, 254], a prediction
+ *     outside [0, n)) cannot be returned synchronously: they set bits in the
+ *     caller's `err_flag` word on the device (SIMT_ERRBIT_*), the offending
+ *     pixel is skipped, and the head additionally poisons its loss with NaN.
+ */
+#ifndef SIMT_B200_H_
+#define SIMT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMT_B200_ABI_VERSION 1
+
+enum {
+  SIMT_EINVAL      = -1,  /* bad argument (null pointer, non-positive size, ...) */
+  SIMT_EUNSUPPORTED = -2, /* shape outside what the kernels are built for      */
+  SIMT_EWORKSPACE  = -3,  /* workspace too small                                */
+  SIMT_ENOSMEM     = -4   /* tile does not fit in shared memory                 */
+};
+
+#define SIMT_ERRBIT_LABEL_RANGE 1 /* head: label not ignore and not in [0, C)        */
+#define SIMT_ERRBIT_PRED_RANGE  2 /* histograms: n_cols*a+b outside [0, rows*cols)   */
+
+int         simt_b200_abi_version(void);
+const char* simt_b200_strerror(int code);
+
+/* Measurement hook (bench.py): while enabled, every head / histogram entry point records a pair
+ * of CUDA events on the caller's stream right around its dominant kernel.
+ * simt_b200_profile_read synchronises on them, returns the summed device time and the number
+ * of launches since the last read, and resets the counter.  Not thread-safe. */
+void simt_b200_profile_enable(int on);
+int  simt_b200_profile_read(double* total_ms_host, long long* launches_host);
+
+/* ------------------------------------------------------------------------- *
+ * The fused head.  Replaces, per head, tools/trainV2_simt.py:371-372 (bilinear
+ * upsample, align_corners=True, built at :301), :402/:405 (same-size upsample
+ * [identity], channel softmax, NHWC flatten), :403/:406 (torch.mm with T),
+ * :408-409 (CrossEntropy2d(is_softmax=False), utils/loss.py:14-40) and the
+ * autograd backward of those lines triggered at :428.
+ *
+ *   logits  [B, CK, h, w] f32 contiguous (DeepLab classifier output, CK = C + K)
+ *   T       [CK, C] f32 row-major (model/deeplab_multi.py:259-263), or NULL for
+ *           the identity (then C must equal CK): plain CE on the upsampled
+ *           logits, i.e. seg_loss at trainV2_simt.py:394-395 /
+ *           trainV1_warmup.py:222-224 and CrossEntropy2d(is_softmax=True)
+ *   labels  [B, H, W]; label_bytes = 1 (uint8, fast path) or 8 (int64, the
+ *           dtype the reference passes, trainV2_simt.py:348).  Valid pixel:
+ *           label >= 0 and label != ignore (utils/loss.py:29)
+ *   stats   [2 + CK*C] f64:  stats[0] = sum over valid pixels of -log q_y,
+ *           stats[1] = number of valid pixels, stats[2 + k*C + c] = UNNORMALISED
+ *           dT[k][c] = -sum_{valid, y=c} p_k / q_y  (zero-filled for simt_head_fwd).
+ *           One f64 buffer so that a sharded run needs ONE all-reduce(sum).
+ *   loss_mean [1] f32: stats[0] / stats[1] (NaN if no valid pixel, as the reference;
+ *           NaN if a label was out of range)
+ *   workspace: simt_head_workspace_bytes() bytes, zero-filled ONCE by the caller
+ *           before first use; the library leaves it zeroed after every call.
+ * ------------------------------------------------------------------------- */
+size_t simt_head_workspace_bytes(int B, int CK, int C, int h, int w, int H, int W);
+
+/* forward only (eval / no-grad) */
+int simt_head_fwd(const float* logits, int B, int CK, int h, int w,
+                  const float* T, int C,
+                  const void* labels, int label_bytes, int H, int W, int ignore,
+                  double* stats, float* loss_mean, int* err_flag,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* single pass forward + backward.  dlogits_raw [B, CK, h, w] receives the
+ * UNNORMALISED gradient sum_pixels U^T (p_k - p_k T[k,y]/q_y) (U = the bilinear
+ * operator, transposed in-kernel); it is zeroed by the call.  Multiply by
+ * grad_out / n_valid (simt_head_scale) once n_valid is known globally. */
+int simt_head_fwdbwd(const float* logits, int B, int CK, int h, int w,
+                     const float* T, int C,
+                     const void* labels, int label_bytes, int H, int W, int ignore,
+                     float* dlogits_raw, double* stats, float* loss_mean, int* err_flag,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* two-pass backward with a scale already known on the host:
+ * dlogits = scale * raw, dT [CK, C] f32 = scale * raw dT.  (scale = grad_out / n_valid) */
+int simt_head_bwd(const float* logits, int B, int CK, int h, int w,
+                  const float* T, int C,
+                  const void* labels, int label_bytes, int H, int W, int ignore,
+                  float scale, float* dlogits, float* dT, int* err_flag,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* epilogue of the single-pass variant, no host sync:
+ *   s = (grad_out ? *grad_out : 1) / stats[1];  dlogits[i] *= s;  dT[k][c] = s * stats[2 + k*C + c]
+ * `stats` may be the all-reduced buffer of a sharded run. */
+int simt_head_scale(float* dlogits, long long n_dlogits, const double* stats, int CK, int C,
+                    const float* grad_out, float* dT, void* stream);
+
+/* tuning hook for benchmarks (process-global, not thread-safe): tile size in
+ * low-res cells, threads per CTA, lanes per pixel-run (1, 2 or 4); 0 = automatic. */
+void simt_head_set_tuning(int tile_cells_y, int tile_cells_x, int threads, int lanes_per_run);
+
+/* ------------------------------------------------------------------------- *
+ * CrossEntropy2d(is_softmax=False) on already-mixed probabilities, for callers
+ * that keep the reference's unfused lines: utils/loss.py:14-40 forward
+ * (-mean log prob[b, y, i, j] over valid pixels) and its backward.
+ *   prob [B, C, H, W] f32;  stats [2] f64 = {sum -log, n_valid}
+ *   simt_nll2d_bwd: dprob (zeroed by the call) [b, y, i, j] = -(grad_out / n_valid) / prob
+ * ------------------------------------------------------------------------- */
+int simt_nll2d_fwd(const float* prob, int B, int C, int H, int W,
+                   const void* labels, int label_bytes, int ignore,
+                   double* stats, float* loss_mean, int* err_flag, void* stream);
+int simt_nll2d_bwd(const float* prob, int B, int C, int H, int W,
+                   const void* labels, int label_bytes, int ignore,
+                   const double* stats, const float* grad_out, float* dprob, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Integer eval histograms (bit-exact).
+ *
+ * simt_confusion: hist[n_cols*a' + b] += 1 for every pixel with 0 <= a' < n_rows,
+ * where a' = lut256 ? lut256[a] : a.  Replaces tools/compute_iou.py:9-11
+ * fast_hist(a, b, n) (n_rows = n_cols = n; dup tools/evaluate_cityscapes.py:81-83),
+ * tools/compute_ConfusionMatrix.py:54-56 fast_hist(a, b, n33, n19), and -- through
+ * the LUT -- tools/compute_iou.py:18-22 label_mapping fused in front of it.  Like
+ * numpy.bincount on n*a+b, an out-of-range b that still lands inside the table is
+ * counted where it lands; an index outside the table (numpy raises) sets
+ * SIMT_ERRBIT_PRED_RANGE and is skipped.
+ *   a, b: [n] uint8 (a_bytes/b_bytes = 1, fast path) or int64 (= 8)
+ *   lut256: 256-byte table on the device or NULL (only with a_bytes = 1)
+ *   hist: [n_rows*n_cols] int64, ACCUMULATED into (the reference's `hist +=`,
+ *   compute_iou.py:51)
+ *
+ * simt_class_hist: hist[a] += 1 for 0 <= a < n_bins.  Replaces
+ * tools/compute_ClassDistribution.py:52-54 fast_hist(a, n).
+ *
+ * simt_label_map: out[i] = lut256[in[i]] as int64 (compute_iou.py:18-22).
+ * ------------------------------------------------------------------------- */
+int simt_confusion(const void* a, int a_bytes, const void* b, int b_bytes, long long n,
+                   const uint8_t* lut256, int n_rows, int n_cols,
+                   long long* hist, int* err_flag, void* stream);
+int simt_class_hist(const void* a, int a_bytes, long long n, int n_bins,
+                    long long* hist, void* stream);
+int simt_label_map(const uint8_t* in, long long n, const uint8_t* lut256, long long* out, void* stream);
+
+/* benchmark hook: 0 = automatic, 1 = lane-private byte counters, 2 = shared atomics */
+void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMT_B200_H_ */

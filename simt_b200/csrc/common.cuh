@@ -1,0 +1,73 @@
+// Shared helpers for the simt_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/simt_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "simt_b200 is written for sm_100a (B200) only"
+#endif
+
+#define SIMT_CUDA_TRY(expr)                     \
+  do {                                          \
+    cudaError_t e__ = (expr);                   \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+
+namespace simt {
+
+struct DeviceInfo {
+  int sm_count;
+  int smem_optin;  // max dynamic shared memory per CTA (bytes)
+};
+
+// Per-device cache (the only global state besides the tuning hooks).
+inline int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  static bool have[64] = {};
+  int dev = 0;
+  SIMT_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return SIMT_EUNSUPPORTED;
+  if (!have[dev]) {
+    DeviceInfo d;
+    SIMT_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SIMT_CUDA_TRY(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache[dev] = d;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return 0;
+}
+
+// launch profiler (capi.cu)
+bool prof_enabled();
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 128-bit streaming load that does not allocate in L1 (data is touched once).
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace simt

@@ -1,0 +1,194 @@
+"""The fused SimT head as a torch.autograd.Function over the C ABI.
+
+Replaces, per head, the reference lines tools/trainV2_simt.py:371-372 (upsample),
+:402-403 / :405-406 (identity upsample, softmax, NHWC flatten, mm with T) and
+:408-409 (``CrossEntropy2d(is_softmax=False)``, utils/loss.py:14-40), plus their
+autograd backward (:428):
+
+    loss_y = simt_head(pred_lo, T, label_target, (H, W))
+
+PyTorch is used for device memory, streams and torch.distributed only; all
+arithmetic is in libsimt_b200.so.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_WORKSPACES = {}
+_ERRFLAGS = {}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (dev.index, _stream_ptr())
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def error_flag(dev) -> torch.Tensor:
+    """Per-device int32 word the kernels OR their SIMT_ERRBIT_* bits into."""
+    dev = torch.device(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    f = _ERRFLAGS.get(idx)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+        _ERRFLAGS[idx] = f
+    return f
+
+
+def check_errors(dev=None) -> None:
+    """Synchronise and raise if a kernel flagged a contract violation (the reference raises
+    IndexError / a device-side assert for a label in [C, 254], and numpy raises ValueError for an
+    out-of-table prediction).  Clears the flag."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else torch.device(dev)
+    f = error_flag(dev)
+    v = int(f.item())
+    if v:
+        f.zero_()
+        what = []
+        if v & 1:
+            what.append("label outside [0, C) that is not the ignore label")
+        if v & 2:
+            what.append("n_cols*a+b outside the histogram table")
+        raise IndexError("simt_b200: " + "; ".join(what))
+
+
+def _check_inputs(logits, T, labels, out_size):
+    if not (isinstance(logits, torch.Tensor) and logits.is_cuda):
+        raise RuntimeError("simt_b200 runs on CUDA (sm_100a) only: logits must be a CUDA tensor; there is no CPU fallback")
+    if logits.dtype != torch.float32 or logits.dim() != 4:
+        raise TypeError("logits must be float32 [B, CK, h, w]")
+    if labels.dim() != 3 or labels.size(0) != logits.size(0):
+        raise ValueError(f"labels must be [B, H, W] with B={logits.size(0)}, got {tuple(labels.shape)}")
+    if labels.dtype not in (torch.uint8, torch.int64):
+        raise TypeError("labels must be uint8 (fast path) or int64 (the reference's dtype)")
+    if labels.device != logits.device:
+        raise RuntimeError("labels and logits must be on the same device")
+    H, W = int(out_size[0]), int(out_size[1])
+    if (labels.size(1), labels.size(2)) != (H, W):
+        raise ValueError(f"{labels.size(1)}x{labels.size(2)} labels vs out_size {H}x{W}")
+    CK = logits.size(1)
+    if T is not None:
+        if T.dim() != 2 or T.size(0) != CK:
+            raise ValueError(f"T must be [CK={CK}, C], got {tuple(T.shape)}")
+        if T.dtype != torch.float32 or T.device != logits.device:
+            raise TypeError("T must be float32 on the logits' device")
+    return H, W
+
+
+def head_forward_raw(logits, T, labels, out_size, ignore=255, need_grad=True):
+    """One launch of the fused kernel.  Returns (stats f64[2+CK*C], loss_mean f32[], dlogits_raw or None)."""
+    lib = _lib.load()
+    H, W = _check_inputs(logits, T, labels, out_size)
+    logits = logits.contiguous()
+    labels = labels.contiguous()
+    Tc = None if T is None else T.detach().contiguous()
+    B, CK, h, w = logits.shape
+    C = CK if Tc is None else Tc.size(1)
+    dev = logits.device
+    nws = lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W)
+    ws = _workspace(dev, nws)
+    stats = torch.empty(2 + CK * C, dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    err = error_flag(dev)
+    lb = 1 if labels.dtype == torch.uint8 else 8
+    tptr = None if Tc is None else Tc.data_ptr()
+    with torch.cuda.device(dev):
+        if need_grad:
+            dl = torch.empty_like(logits)
+            rc = lib.simt_head_fwdbwd(logits.data_ptr(), B, CK, h, w, tptr, C, labels.data_ptr(), lb, H, W, int(ignore),
+                                      dl.data_ptr(), stats.data_ptr(), loss.data_ptr(), err.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream_ptr())
+            _lib.check(rc, "simt_head_fwdbwd")
+        else:
+            dl = None
+            rc = lib.simt_head_fwd(logits.data_ptr(), B, CK, h, w, tptr, C, labels.data_ptr(), lb, H, W, int(ignore),
+                                   stats.data_ptr(), loss.data_ptr(), err.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr())
+            _lib.check(rc, "simt_head_fwd")
+    return stats, loss, dl
+
+
+def head_scale(dl_raw, stats, CK, C, grad_out, want_dT=True):
+    """dlogits = raw * grad_out / n_valid (in place), dT = stats[2:] * grad_out / n_valid."""
+    lib = _lib.load()
+    dev = dl_raw.device
+    dT = torch.empty(CK, C, dtype=torch.float32, device=dev) if want_dT else None
+    g = None
+    if grad_out is not None:
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.simt_head_scale(dl_raw.data_ptr(), dl_raw.numel(), stats.data_ptr(), CK, C,
+                                 None if g is None else g.data_ptr(), None if dT is None else dT.data_ptr(),
+                                 _stream_ptr())
+    _lib.check(rc, "simt_head_scale")
+    return dl_raw, dT
+
+
+class _SimTHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, T, labels, out_size, ignore, group):
+        need_grad = logits.requires_grad or (T is not None and T.requires_grad)
+        stats, loss, dl = head_forward_raw(logits.detach(), T, labels, out_size, ignore, need_grad)
+        if group is not None:
+            # batch-sharded run: ONE all-reduce(sum) of {loss_sum, n_valid, raw dT} (2.9 KB at CK=C=19)
+            import torch.distributed as dist
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            loss = (stats[0] / stats[1]).to(torch.float32)
+        ctx.has_T = T is not None
+        ctx.shape_T = None if T is None else tuple(T.shape)
+        ctx.consumed = False
+        ctx.save_for_backward(stats, dl if dl is not None else torch.empty(0, device=logits.device))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        stats, dl = ctx.saved_tensors
+        if dl.numel() == 0:
+            return None, None, None, None, None, None
+        if ctx.consumed:
+            raise RuntimeError("simt_head: backward through the fused head a second time "
+                               "(its raw gradient buffer is scaled in place)")
+        ctx.consumed = True
+        CK = dl.size(1)
+        C = ctx.shape_T[1] if ctx.has_T else CK
+        dlog, dT = head_scale(dl, stats, CK, C, grad_out, want_dT=ctx.has_T)
+        return dlog, dT, None, None, None, None
+
+
+def simt_head(logits_lo: torch.Tensor, T: Optional[torch.Tensor], labels: torch.Tensor,
+              out_size: Optional[Tuple[int, int]] = None, ignore: int = 255, group=None) -> torch.Tensor:
+    """T-corrected per-pixel loss of one DeepLab head, fused.
+
+    Equals ``CrossEntropy2d(is_softmax=False)(mm(softmax(interp(interp(logits_lo))), T), labels)``
+    of the reference (tools/trainV2_simt.py:371-372,402-409) to 1e-5 relative; gradients flow to
+    ``logits_lo`` (low resolution) and ``T``.  ``T=None`` gives plain CE on the upsampled logits
+    (:394-395).  ``labels`` uint8 or int64 [B, H, W]; ``group``: a torch.distributed process group
+    for a batch-sharded run (mean over the GLOBAL valid-pixel count, dT summed over ranks).
+    """
+    if out_size is None:
+        out_size = (labels.size(1), labels.size(2))
+    return _SimTHeadFn.apply(logits_lo, T, labels, tuple(out_size), int(ignore), group)
+
+
+class SimTHead(torch.nn.Module):
+    """Module form: ``SimTHead((H, W))(logits_lo, T, labels)``; holds no parameters."""
+
+    def __init__(self, out_size=None, ignore_label: int = 255, group=None):
+        super().__init__()
+        self.out_size = out_size
+        self.ignore_label = ignore_label
+        self.group = group
+
+    def forward(self, logits_lo, T, labels):
+        return simt_head(logits_lo, T, labels, self.out_size, self.ignore_label, self.group)

@@ -1,0 +1,207 @@
+"""GPU parity of the fused head: CUDA path (public API -> ctypes -> C ABI) vs golden vectors
+from the reference and vs the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): loss, dLogits, dT within 1e-5 relative of the fp32
+reference -- norm-wise (||d||_2 / ||ref||_2) and max-abs-scaled, since element-wise relative
+error is ill-posed at zeros.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import HEAD_CASES, class_dist, load_golden, rel_l2, rel_max, run_gpu_head
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _check(got, ref, what):
+    assert rel_l2(got, ref) <= TOL, f"{what}: rel l2 {rel_l2(got, ref):.3e}"
+    assert rel_max(got, ref) <= TOL, f"{what}: rel max {rel_max(got, ref):.3e}"
+
+
+@pytest.mark.parametrize("name", HEAD_CASES)
+@pytest.mark.parametrize("int64_labels", [False, True])
+def test_head_vs_reference_golden(name, int64_labels):
+    g = load_golden(name)
+    loss, dl, dT = run_gpu_head(g["logits"], g["T"], g["labels"], g["size"], int64_labels)
+    assert abs(float(loss) - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _check(dl, g["dlogits_f32"], "dlogits vs fp32 reference")
+    _check(dT, g["dT_f32"], "dT vs fp32 reference")
+    # and at least as close to the fp64 truth as 1e-5
+    _check(dl, g["dlogits_f64"], "dlogits vs fp64 reference")
+    _check(dT, g["dT_f64"], "dT vs fp64 reference")
+
+
+@pytest.mark.parametrize("lpr", [1, 2])
+@pytest.mark.parametrize("tile", [(8, 8), (4, 8), (2, 4), (1, 1), (3, 16)])
+def test_head_tilings_and_lane_splits_agree(lpr, tile):
+    """Every tiling / lanes-per-run configuration is the same function."""
+    from simt_b200 import _lib
+    g = load_golden("head_cfg1_tile")
+    lib = _lib.load()
+    try:
+        lib.simt_head_set_tuning(tile[0], tile[1], 0, lpr)
+        loss, dl, dT = run_gpu_head(g["logits"], g["T"], g["labels"], g["size"])
+    finally:
+        lib.simt_head_set_tuning(0, 0, 0, 0)
+    assert abs(float(loss) - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _check(dl, g["dlogits_f32"], "dlogits")
+    _check(dT, g["dT_f32"], "dT")
+
+
+@pytest.mark.parametrize("B,K,coherent", [(1, 0, True), (1, 0, False), (2, 4, True), (1, 15, True)])
+def test_head_config_shapes_vs_oracle(B, K, coherent):
+    """BASELINE configs 1-3 at full 65x129 -> 512x1024 resolution against the CPU oracle (seconds)."""
+    from oracle import simt_oracle as O
+    CK = 19 + K
+    logits, labels = O.synth_head_inputs(B, CK, 65, 129, 512, 1024, seed=1234, coherent=coherent,
+                                         class_dist=class_dist())
+    torch.manual_seed(1234)
+    NTM = torch.nn.init.kaiming_normal_(torch.ones(CK, 19), mode="fan_out", nonlinearity="relu")
+    T = O.sig_ntm_forward(NTM, class_dist(), 19, K)
+    lo, dlo, dTo = O.simt_head_fwd_bwd(logits, T, labels, (512, 1024), torch.float32)
+    loss, dl, dT = run_gpu_head(logits.numpy(), T.numpy(), labels.numpy(), (512, 1024))
+    assert abs(float(loss) - float(lo)) <= TOL * abs(float(lo))
+    _check(dl, dlo.numpy(), "dlogits")
+    _check(dT, dTo.numpy(), "dT")
+
+
+def test_plain_ce_T_none_vs_oracle():
+    """T = None is torch's CrossEntropyLoss(ignore_index=255) on the upsampled logits (trainV2_simt.py:394)."""
+    from oracle import simt_oracle as O
+    logits, labels = O.synth_head_inputs(2, 19, 9, 17, 64, 128, seed=5, coherent=True, block=8)
+    lg = logits.clone().requires_grad_(True)
+    ref = O.plain_ce_loss(lg, labels.long(), (64, 128))
+    ref.backward()
+    loss, dl, _ = run_gpu_head(logits.numpy(), None, labels.numpy(), (64, 128))
+    assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
+    _check(dl, lg.grad.numpy(), "dlogits")
+
+
+def test_forward_only_and_two_pass_backward_agree_with_single_pass():
+    import simt_b200
+    from simt_b200 import _lib, head
+    g = load_golden("head_openset4")
+    dev = torch.device("cuda")
+    lg = torch.from_numpy(g["logits"]).to(dev)
+    T = torch.from_numpy(g["T"]).to(dev)
+    lab = torch.from_numpy(g["labels"]).to(dev)
+    size = tuple(int(s) for s in g["size"])
+    with torch.no_grad():
+        l_fwd = simt_b200.simt_head(lg, T, lab, size)
+    assert abs(float(l_fwd) - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    # two-pass C entry: scale known on the host
+    lib = _lib.load()
+    stats, _, _ = head.head_forward_raw(lg, T, lab, size, need_grad=False)
+    n_valid = float(stats[1])
+    B, CK, h, w = lg.shape
+    C = T.shape[1]
+    dl = torch.empty_like(lg)
+    dT = torch.empty_like(T)
+    ws = torch.zeros(lib.simt_head_workspace_bytes(B, CK, C, h, w, *size), dtype=torch.uint8, device=dev)
+    rc = lib.simt_head_bwd(lg.data_ptr(), B, CK, h, w, T.data_ptr(), C, lab.data_ptr(), 1, size[0], size[1], 255,
+                           1.0 / n_valid, dl.data_ptr(), dT.data_ptr(), head.error_flag(dev).data_ptr(),
+                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    _check(dl.cpu().numpy(), g["dlogits_f32"], "two-pass dlogits")
+    _check(dT.cpu().numpy(), g["dT_f32"], "two-pass dT")
+
+
+def test_grad_output_scaling_and_second_backward():
+    import simt_b200
+    g = load_golden("head_small_r")
+    dev = torch.device("cuda")
+    lg = torch.from_numpy(g["logits"]).to(dev).requires_grad_(True)
+    T = torch.from_numpy(g["T"]).to(dev).requires_grad_(True)
+    lab = torch.from_numpy(g["labels"]).to(dev)
+    loss = simt_b200.simt_head(lg, T, lab, tuple(int(s) for s in g["size"]))
+    (0.1 * loss).backward(retain_graph=True)        # lambda_seg = 0.1 on head 1 (trainV2_simt.py:423)
+    _check(lg.grad.cpu().numpy(), 0.1 * g["dlogits_f32"], "scaled dlogits")
+    _check(T.grad.cpu().numpy(), 0.1 * g["dT_f32"], "scaled dT")
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+
+
+def test_edge_cases():
+    import simt_b200
+    dev = torch.device("cuda")
+    lg = torch.randn(1, 19, 5, 9, device=dev, requires_grad=True)
+    T = torch.softmax(torch.randn(19, 19, device=dev), 1)
+    # all ignored -> NaN, like the reference's mean over an empty selection
+    lab = torch.full((1, 32, 64), 255, dtype=torch.uint8, device=dev)
+    assert torch.isnan(simt_b200.simt_head(lg, T, lab, (32, 64)))
+    # negative int64 labels are ignored (utils/loss.py:29)
+    lab64 = torch.randint(0, 19, (1, 32, 64), device=dev)
+    lab_neg = lab64.clone()
+    lab_neg[0, :16] = -1
+    lab_ign = lab64.clone()
+    lab_ign[0, :16] = 255
+    assert float(simt_b200.simt_head(lg, T, lab_neg, (32, 64))) == float(simt_b200.simt_head(lg, T, lab_ign, (32, 64)))
+    # a label in [C, 254] is a contract violation: loss poisoned with NaN + IndexError on check
+    bad = lab64.clone()
+    bad[0, 3, 3] = 77
+    out = simt_b200.simt_head(lg, T, bad, (32, 64))
+    assert torch.isnan(out)
+    with pytest.raises(IndexError):
+        simt_b200.check_errors()
+    simt_b200.check_errors()      # flag cleared
+    # huge dynamic range: the run-level softmax bound must fall back to the exact max
+    big = torch.zeros(1, 19, 2, 2, device=dev)
+    big[0, 0, 0, 0] = 3000.0
+    big[0, 1, :, :] = -3000.0
+    big[0, 2, 1, 1] = 2500.0
+    labs = torch.randint(0, 19, (1, 16, 16), device=dev).to(torch.uint8)
+    ref_in = big.cpu().double().requires_grad_(True)
+    from oracle import simt_oracle as O
+    ref = O.simt_head_loss(ref_in, T.cpu().double(), labs.cpu().long(), (16, 16))
+    got = simt_b200.simt_head(big, T, labs, (16, 16))
+    assert torch.isfinite(got)
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+
+
+def test_deterministic_loss_and_dT():
+    g = load_golden("head_cfg1_tile")
+    a = run_gpu_head(g["logits"], g["T"], g["labels"], g["size"])
+    b = run_gpu_head(g["logits"], g["T"], g["labels"], g["size"])
+    assert a[0].tobytes() == b[0].tobytes()
+
+
+def test_crossentropy2d_dropin_both_modes():
+    import simt_b200
+    g = load_golden("ce2d")
+    dev = torch.device("cuda")
+    y = torch.from_numpy(g["y"]).to(dev)
+    for mode in (1, 0):
+        x = torch.from_numpy(g["x"])
+        xin = (x if mode else torch.softmax(x, 1)).to(dev).requires_grad_(True)
+        crit = simt_b200.CrossEntropy2d(is_softmax=bool(mode)).cuda()
+        loss = crit(xin, y)
+        loss.backward()
+        ref = g[f"loss_softmax{mode}"]
+        assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref)), mode
+        _check(xin.grad.cpu().numpy(), g[f"grad_softmax{mode}"], f"grad mode {mode}")
+
+
+def test_reference_training_lines_with_fused_head():
+    """The reference's unfused lines on torch-CUDA vs the fused op, same device, same tensors."""
+    import torch.nn as nn
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    logits, labels = O.synth_head_inputs(2, 23, 33, 65, 256, 512, seed=77, coherent=True, class_dist=class_dist())
+    torch.manual_seed(3)
+    ntm = simt_b200.sig_NTM(19, 4).to(dev)
+    lg1 = logits.to(dev).requires_grad_(True)
+    T1 = ntm()
+    ref = O.simt_head_loss(lg1, T1, labels.to(dev).long(), (256, 512))
+    ref.backward()
+    g_ref, n_ref = lg1.grad.clone(), ntm.NTM.grad.clone()
+    ntm.NTM.grad = None
+    lg2 = logits.to(dev).requires_grad_(True)
+    out = simt_b200.simt_head(lg2, ntm(), labels.to(dev), (256, 512))
+    out.backward()
+    assert abs(float(out) - float(ref)) <= TOL * abs(float(ref))
+    _check(lg2.grad.cpu().numpy(), g_ref.cpu().numpy(), "dlogits vs torch-CUDA eager")
+    _check(ntm.NTM.grad.cpu().numpy(), n_ref.cpu().numpy(), "dNTM vs torch-CUDA eager")

@@ -1,0 +1,129 @@
+"""GPU parity of the integer histograms: bit-exact against the reference golden vectors and the
+numpy oracle, including the reference's edge cases."""
+import numpy as np
+import pytest
+import torch
+
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_confusion_label_mapping_miou():
+    import simt_b200
+    g = load_golden("hist")
+    mapping = g["mapping"]
+    meter = simt_b200.ConfusionMeter(19, mapping=mapping)
+    hist = np.zeros((19, 19), dtype=np.int64)
+    for gt, pr in zip(g["gt"], g["pred"]):
+        meter.update(gt, pr)                                   # fused LUT + confusion
+        lab = simt_b200.label_mapping(gt, mapping)             # the unfused drop-in pair
+        assert lab.dtype == np.int64 and lab.shape == gt.shape
+        hist += simt_b200.fast_hist(lab.flatten(), pr.flatten(), 19)
+    assert np.array_equal(hist, g["hist19"])
+    assert np.array_equal(meter.value(), g["hist19"])
+    assert meter.miou_percent() == float(g["miou"])
+    iu = simt_b200.per_class_iu(hist)
+    assert np.array_equal(np.nan_to_num(iu, nan=-1), np.nan_to_num(g["iu"], nan=-1))
+    assert np.array_equal(simt_b200.fast_hist(g["gt"][0].flatten(), g["pred"][0].flatten(), 34, 19), g["rect34x19"])
+    assert np.array_equal(simt_b200.fast_hist(g["pred"][0].flatten(), 19), g["class19"])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("coherent", [True, False])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4099, 1 << 20, (1 << 21) + 5])
+def test_confusion_vs_oracle_sizes(mode, coherent, n):
+    import simt_b200
+    from simt_b200 import _lib
+    from oracle import simt_oracle as O
+    side = max(1, int(np.ceil(np.sqrt(max(n, 1)))))
+    gt, pr = O.synth_eval_pair(side, side, seed=n % 97 + 3, coherent=coherent, block=16)
+    gt, pr = gt.reshape(-1)[:n], pr.reshape(-1)[:n]
+    lut = simt_b200.build_lut(O.CITYSCAPES_LABEL2TRAIN)
+    ref = O.fast_hist(O.label_mapping(gt, np.array(O.CITYSCAPES_LABEL2TRAIN)), pr, 19)
+    lib = _lib.load()
+    try:
+        lib.simt_hist_set_tuning(mode, 0, 0)
+        m = simt_b200.ConfusionMeter(19, mapping=O.CITYSCAPES_LABEL2TRAIN)
+        m.update(gt, pr)
+        m.update(gt, pr)                       # accumulates like `hist +=`
+        got = m.value()
+    finally:
+        lib.simt_hist_set_tuning(0, 0, 0)
+    assert np.array_equal(got, 2 * ref)
+    assert lut.dtype == np.uint8
+
+
+@pytest.mark.parametrize("unroll,warps", [(1, 4), (2, 8), (4, 16)])
+def test_confusion_tunings_agree(unroll, warps):
+    import simt_b200
+    from simt_b200 import _lib
+    from oracle import simt_oracle as O
+    gt, pr = O.synth_eval_pair(512, 1024, seed=9, coherent=True)
+    ref = O.fast_hist_rect(gt.reshape(-1), pr.reshape(-1), 34, 19)
+    lib = _lib.load()
+    try:
+        lib.simt_hist_set_tuning(1, warps, unroll)
+        got = simt_b200.fast_hist(gt.reshape(-1), pr.reshape(-1), 34, 19)
+    finally:
+        lib.simt_hist_set_tuning(0, 0, 0)
+    assert np.array_equal(got, ref)
+
+
+def test_worst_case_contention_and_byte_counter_overflow():
+    """One bin gets every pixel (road is 41 % of real labels): private 8-bit counters must fold in time."""
+    import simt_b200
+    n = 5_000_011
+    a = np.zeros(n, dtype=np.uint8)
+    b = np.full(n, 3, dtype=np.uint8)
+    a[::7919] = 5                              # break the uniform fast path now and then
+    got = simt_b200.fast_hist(a, b, 19)
+    ref = np.zeros((19, 19), dtype=np.int64)
+    ref[5, 3] = len(a[::7919])
+    ref[0, 3] = n - ref[5, 3]
+    assert np.array_equal(got, ref)
+    # alternating pattern defeats every fast path and hammers two bins
+    a = (np.arange(n) & 1).astype(np.uint8)
+    got = simt_b200.fast_hist(a, np.zeros(n, dtype=np.uint8), 19)
+    assert got[0, 0] == (n + 1) // 2 and got[1, 0] == n // 2 and got.sum() == n
+
+
+def test_int64_inputs_and_masks():
+    import simt_b200
+    from oracle import simt_oracle as O
+    rng = np.random.default_rng(0)
+    a = rng.integers(-3, 300, size=100_003).astype(np.int64)       # negatives and >= n are masked
+    b = rng.integers(0, 19, size=100_003).astype(np.int64)
+    assert np.array_equal(simt_b200.fast_hist(a, b, 19), O.fast_hist(a, b, 19))
+    a8 = rng.integers(0, 256, size=100_003).astype(np.uint8)
+    assert np.array_equal(simt_b200.fast_hist(a8, 19), O.class_hist(a8, 19))
+    assert np.array_equal(simt_b200.fast_hist(a, 19), O.class_hist(a, 19))
+    # misaligned views take the generic kernel
+    assert np.array_equal(simt_b200.fast_hist(torch.from_numpy(a8).cuda()[3:], torch.from_numpy(b).cuda()[3:].to(torch.uint8), 19).cpu().numpy(),
+                          O.fast_hist(a8[3:].astype(np.int64), b[3:], 19))
+
+
+def test_reference_aliasing_quirk_and_out_of_table_error():
+    import simt_b200
+    from oracle import simt_oracle as O
+    a = np.array([0, 1, 2] * 11, dtype=np.uint8)
+    b = np.array([0, 20, 1] * 11, dtype=np.uint8)
+    assert np.array_equal(simt_b200.fast_hist(a, b, 19), O.fast_hist(a, b, 19))     # b >= n aliases, like numpy
+    with pytest.raises(IndexError):                                                   # numpy: ValueError on reshape
+        simt_b200.fast_hist(np.array([18] * 40, dtype=np.uint8), np.array([30] * 40, dtype=np.uint8), 19)
+
+
+def test_full_resolution_eval_image_bit_exact_miou():
+    """BASELINE config 4 shape (2048x1024 per image) on a few images; mIoU string bit-exact."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    mapping = np.array(O.CITYSCAPES_LABEL2TRAIN)
+    meter = simt_b200.ConfusionMeter(19, mapping=mapping)
+    ref = np.zeros((19, 19), dtype=np.int64)
+    for i in range(3):
+        gt, pr = O.synth_eval_pair(1024, 2048, seed=40 + i, coherent=(i < 2))
+        meter.update(gt, pr)
+        ref += O.fast_hist(O.label_mapping(gt, mapping).flatten(), pr.flatten(), 19)
+    assert np.array_equal(meter.value(), ref)
+    assert meter.miou_percent() == O.miou_percent(ref)
+    assert int(meter.value().sum()) == int((O.label_mapping(gt, mapping) < 19).sum() * 0 + ref.sum())
