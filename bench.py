@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Contract benchmark: labeled pixels/sec of the fused SimT head fwd+bwd on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch (BASELINE.json configs[1]: batch 8 per
+GPU, logits 19x65x129 -> 512x1024, C = 19 T-corrected CE, forward + backward):
+    memset(dLogits) -> fused fwd/bwd kernel -> finalize -> [all-reduce of the 2.9 KB stats buffer
+    when N > 1] -> scale kernel (dLogits, dT *= 1 / N_valid).
+`value`  : inputs already resident in HBM (rotating input sets larger than L2), timed with CUDA
+           events, barrier + synchronize on both sides, max over ranks.
+`e2e`    : the same metric through the public autograd API (simt_b200.simt_head + backward) with
+           HOST inputs: per step a pinned-host -> device copy of logits and labels and a
+           device -> host read of the loss are inside the timed region.
+`roofline`: algorithmic HBM bytes of the fused kernel / its mean launch duration, measured with
+           CUDA events recorded around that kernel on its stream during the timed steps.
+`cpu_baseline` / `--impl reference`: the reference's own CPU PyTorch path (oracle port of
+           tools/trainV2_simt.py:371-372,402-409 + utils/loss.py, see oracle/simt_oracle.py)
+           timed on this box's host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, C, K_OPEN, h, w, H, W = 8, 19, 0, 65, 129, 512, 1024
+CK = C + K_OPEN
+METRIC = "labeled_pixels_per_sec_fwd_bwd_simt_head"
+UNIT = "labeled px/s"
+WORKLOAD = (f"batch {B_PER_GPU}/GPU, logits {CK}x{h}x{w} -> {H}x{W} bilinear align_corners, C={C} T-matrix CE "
+            f"fwd+bwd, uint8 labels ~ClassDist_bapa in 32x32 blocks, 10% ignore=255 (BASELINE configs[1])")
+
+
+def alg_bytes_per_launch(B):
+    """single-pass fwd+bwd = logits read + labels read + dLogits write."""
+    return B * (4 * CK * h * w + H * W + 4 * CK * h * w)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["head_fwdbwd_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons via NVML (what nvidia-smi prints), sampled while the GPU works."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.hd = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.hd, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.hd, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.hd).gpu
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.hd)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.hd)
+                self.samples.append((mhz, util))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        busy = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_inputs(n_sets, seed0, device=None, pin=False):
+    from oracle import simt_oracle as O          # input synthesis only (seeded)
+    cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
+    sets = []
+    for s in range(n_sets):
+        lg, lab = O.synth_head_inputs(B_PER_GPU, CK, h, w, H, W, seed=seed0 + s, coherent=True, class_dist=cd)
+        if device is not None:
+            lg, lab = lg.to(device), lab.to(device)
+        elif pin:
+            lg, lab = lg.pin_memory(), lab.pin_memory()
+        sets.append((lg, lab))
+    return sets
+
+
+def reference_T():
+    import simt_b200
+    torch.manual_seed(1234)
+    return simt_b200.sig_NTM(C, K_OPEN)().detach()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's PyTorch path)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(O, lg, T, lab, nimg):
+    lgi = lg[:nimg].clone().requires_grad_(True)
+    Tt = T.clone().requires_grad_(True)
+    loss = O.simt_head_loss(lgi, Tt, lab[:nimg].long(), (H, W))
+    loss.backward()
+    return float(loss)
+
+
+def run_cpu_baseline(budget_s=20.0):
+    """Bounded sample on this host: full batch, 1 warm-up + as many timed passes as fit (>= 2)."""
+    from oracle import simt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lg, lab = make_inputs(1, 1234)[0]
+    T = reference_T().cpu()
+    nimg = B_PER_GPU
+    t0 = time.perf_counter()
+    cpu_reference_step(O, lg, T, lab, 1)
+    t1 = time.perf_counter() - t0
+    if t1 * nimg * 3 > budget_s:
+        nimg = max(1, int(budget_s / (3 * t1)))
+    best = None
+    t_start = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t_start < budget_s * 0.6 and n < 5):
+        t0 = time.perf_counter()
+        cpu_reference_step(O, lg, T, lab, nimg)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        n += 1
+    labeled = int((lab[:nimg] != 255).sum())
+    return {"value": labeled / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nimg} of {B_PER_GPU} images of the same batch, 1 warm-up + best of {n} passes, "
+                      f"torch {torch.__version__} CPU, {cores} threads"}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from oracle import simt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lg, lab = make_inputs(1, 1234)[0]
+    T = reference_T().cpu()
+    total = args.steps + args.warmup
+    t0 = time.perf_counter()
+    cpu_reference_step(O, lg, T, lab, 1)
+    t_img = time.perf_counter() - t0
+    nimg = int(max(1, min(B_PER_GPU, 150.0 / (max(total, 1) * t_img))))
+    for _ in range(args.warmup):
+        cpu_reference_step(O, lg, T, lab, nimg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(O, lg, T, lab, nimg)
+    dt = time.perf_counter() - t0
+    labeled = int((lab[:nimg] != 255).sum())
+    val = labeled * args.steps / dt
+    sample = (f"{nimg} of {B_PER_GPU} images per step (bounded sample of the same workload), oracle port of the "
+              f"reference's CPU PyTorch path, torch {torch.__version__}, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import simt_b200
+    from simt_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    n_sets = 12          # 12 x (5.1 MB logits + 4.2 MB labels + 5.1 MB dLogits) = 173 MB > 126 MB L2
+    sets = make_inputs(n_sets, 1234 + 1000 * rank, device=dev)
+    labeled_per_set = [int((lab != 255).sum()) for _, lab in sets]
+    T = reference_T().to(dev)
+    # one output buffer set per input set so the dLogits writes also rotate through > L2
+    runners = [simt_b200.HeadRunner(B_PER_GPU, CK, C, h, w, H, W, device=dev, group=group) for _ in range(n_sets)]
+
+    def step(i):
+        lg, lab = sets[i % n_sets]
+        return runners[i % n_sets].step(lg, T, lab)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    lib.simt_b200_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    labeled = 0
+    for i in range(args.steps):
+        step(i)
+        labeled += labeled_per_set[i % n_sets]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kms, klaunches = ctypes.c_double(), ctypes.c_longlong()
+    lib.simt_b200_profile_read(ctypes.byref(kms), ctypes.byref(klaunches))
+    lib.simt_b200_profile_enable(0)
+    simt_b200.check_errors(dev)
+
+    # ---- end to end through the public autograd API with host buffers ---------------------------
+    host_sets = make_inputs(4, 777 + 1000 * rank, pin=True)
+    lg_dev = torch.empty(B_PER_GPU, CK, h, w, device=dev)
+    lab_dev = torch.empty(B_PER_GPU, H, W, dtype=torch.uint8, device=dev)
+    Tp = T.clone().requires_grad_(True)
+
+    def e2e_step(i):
+        lgh, labh = host_sets[i % len(host_sets)]
+        lg_dev.copy_(lgh, non_blocking=True)
+        lab_dev.copy_(labh, non_blocking=True)
+        lg = lg_dev.detach().requires_grad_(True)
+        Tp.grad = None
+        loss = simt_b200.simt_head(lg, Tp, lab_dev, (H, W), group=group)
+        loss.backward()
+        return float(loss)          # device -> host read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2e_steps = args.steps
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    g1.record()
+    barrier()
+    per = [int((l != 255).sum()) for _, l in host_sets]
+    e2e_labeled = sum(per[i % len(host_sets)] for i in range(e2e_steps))
+    e2e_ms = g0.elapsed_time(g1)
+
+    # ---- keep the GPU busy a little longer so the clock sampler sees the kernel under load --------
+    if rank == 0 and sampler.ok:
+        t_end = time.perf_counter() + 1.0
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i)
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---- reduce over ranks -------------------------------------------------------------------------
+    vals = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    cnts = torch.tensor([labeled, e2e_labeled], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = (float(x) for x in vals.tolist())
+    labeled_all, e2e_labeled_all = (float(x) for x in cnts.tolist())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        k_avg_ms = kms.value / max(klaunches.value, 1)
+        achieved = alg_bytes_per_launch(B_PER_GPU) / (k_avg_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": labeled_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"batch-sharded x{world}",
+                       "l2": f"inputs and outputs rotate over {n_sets} sets (173 MB per GPU) > 126 MB L2",
+                       "total_px_per_sec": B_PER_GPU * H * W * world * args.steps / (ms_max * 1e-3)},
+            "e2e": {"value": e2e_labeled_all / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": B_PER_GPU * (4 * CK * h * w + H * W), "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
+                    "api": "simt_b200.simt_head(...).backward() with pinned host inputs"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "kernel": "simt::head_kernel<19,1,FWDBWD,uint8>",
+                         "kernel_ms": k_avg_ms, "launches_timed": int(klaunches.value),
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch(B_PER_GPU), "peak_source": peak_src,
+                         "note": "kernel is MUFU/FP32-issue bound, not HBM bound (DESIGN.md): 19 ex2 + 3 MUFU per pixel"},
+            "clocks": sampler.summary(),
+        }
+        if world == 1:
+            out["cpu_baseline"] = run_cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        import subprocess
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

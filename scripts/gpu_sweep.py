@@ -54,7 +54,7 @@ def main():
     out = {"peak_gbs": PEAK, "head": [], "hist": [], "gpu": torch.cuda.get_device_name(0)}
     cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
     H, W, h, w = 512, 1024, 65, 129
-    for (B, K) in ((8, 0), (8, 4), (8, 15), (1, 0)):
+    for (B, K) in ((8, 0), (8, 4), (8, 15), (1, 0)) if 'nohead' not in sys.argv else ():
         CK = 19 + K
         nsets = 12 if B == 8 else 4
         for coherent in (True, False):
@@ -65,13 +65,9 @@ def main():
             torch.manual_seed(1234)
             T = simt_b200.sig_NTM(19, K).to(dev)().detach()
             labeled = float(sum(int((l != 255).sum()) for _, l in sets)) / len(sets)
-            cfgs = [(0, 0, 0)]
-            if coherent or K == 0:
-                cfgs += [(8, 8, 1), (4, 8, 1), (8, 16, 1), (8, 32, 1), (4, 16, 1), (16, 8, 1), (8, 8, 2), (4, 8, 2), (8, 16, 2)]
+            cfgs = [(0, 0, 0), (1, 0, 2), (2, 0, 2), (1, 0, 4), (2, 0, 4)]
             for (tcy, tcx, lpr) in cfgs:
-                if K == 15 and lpr == 1:
-                    continue
-                if K == 4 and lpr == 1 and (tcy, tcx) != (0, 0):
+                if K > 0 and lpr == 2:
                     continue
                 lib.simt_head_set_tuning(tcy, tcx, 0, lpr)
                 try:
@@ -88,16 +84,22 @@ def main():
                 finally:
                     lib.simt_head_set_tuning(0, 0, 0, 0)
             del sets
-    # ---- histograms -----------------------------------------------------------------------
+    if 'nohist' in sys.argv:
+        json.dump(out, open(os.path.join(ROOT, 'gpurun_out', f'sweep_{tag}.json'), 'w'), indent=1)
+        return
+    # ---- histograms: BIG launches (32 images = 64 Mi pixels per launch), 3 rotating sets > L2 ----------
     lut = torch.from_numpy(simt_b200.build_lut(O.CITYSCAPES_LABEL2TRAIN)).to(dev)
-    nimg = 40                                    # 40 x 2 MiB x 2 = 168 MB > L2
+    nimg, nsets = 32, 3
     for coherent in (True, False):
-        gts, prs = [], []
-        for i in range(nimg):
-            gt, pr = O.synth_eval_pair(1024, 2048, seed=i % 8, coherent=coherent)
-            gts.append(torch.from_numpy(gt)); prs.append(torch.from_numpy(pr))
-        gt_all = torch.stack(gts).to(dev).reshape(nimg, -1)
-        pr_all = torch.stack(prs).to(dev).reshape(nimg, -1)
+        gt_sets, pr_sets = [], []
+        for s_ in range(nsets):
+            gts, prs = [], []
+            for i in range(8):
+                gt, pr = O.synth_eval_pair(1024, 2048, seed=8 * s_ + i, coherent=coherent)
+                gts.append(torch.from_numpy(gt)); prs.append(torch.from_numpy(pr))
+            gt_sets.append(torch.stack(gts).repeat(nimg // 8, 1, 1).to(dev).reshape(-1))
+            pr_sets.append(torch.stack(prs).repeat(nimg // 8, 1, 1).to(dev).reshape(-1))
+        npx = gt_sets[0].numel()
         for (rows, cols, use_lut) in ((19, 19, True), (34, 19, False), (19, 1, False)):
             for mode in (1, 2):
                 for warps, unroll in ((8, 4), (8, 2), (16, 2), (16, 4), (4, 4), (16, 1)):
@@ -106,28 +108,30 @@ def main():
                     try:
                         def run(i):
                             if cols == 1:
-                                simt_b200.hist.class_hist_into(hist, pr_all[i], rows)
+                                simt_b200.hist.class_hist_into(hist, pr_sets[i % nsets], rows)
                             else:
-                                simt_b200.hist.confusion_into(hist, gt_all[i], pr_all[i], rows, cols, lut if use_lut else None)
-                        for i in range(3):
+                                simt_b200.hist.confusion_into(hist, gt_sets[i % nsets], pr_sets[i % nsets], rows, cols,
+                                                              lut if use_lut else None)
+                        for i in range(2):
                             run(i)
                         torch.cuda.synchronize()
                         lib.simt_b200_profile_enable(1)
-                        for i in range(nimg):
+                        for i in range(6):
                             run(i)
                         torch.cuda.synchronize()
                         kms, n = prof_read(lib)
                         lib.simt_b200_profile_enable(0)
                         k_ms = kms / n
-                        nbytes = (1 if cols == 1 else 2) * 1024 * 2048
+                        nbytes = (1 if cols == 1 else 2) * npx
                         out["hist"].append(dict(rows=rows, cols=cols, lut=use_lut, coherent=coherent, mode=mode,
                                                 warps=warps, unroll=unroll, kernel_ms=k_ms, gbs=nbytes / k_ms / 1e6,
-                                                frac=nbytes / k_ms / 1e6 / PEAK))
+                                                frac=nbytes / k_ms / 1e6 / PEAK, npx=npx))
                         print(out["hist"][-1], flush=True)
                     except RuntimeError as e:
                         print("skip hist", rows, cols, mode, warps, unroll, e, flush=True)
                     finally:
                         lib.simt_hist_set_tuning(0, 0, 0)
+        del gt_sets, pr_sets
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"sweep_{tag}.json"), "w"), indent=1)
 

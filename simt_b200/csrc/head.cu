@@ -10,28 +10,35 @@
 //     dz_k = (1/N) (p_k - p_k T[k,y] / q)          (high-res, then U^T to low-res)
 //     dT[k,y] += -(1/N) p_k / q
 // Only column y of T is touched per pixel, so there is no GEMM here: the kernel
-// is bound by the MUFU (one ex2 per channel per pixel) and FP32 pipes, not by
-// HBM (5.6 B/pixel algorithmic) -- see DESIGN.md.
+// is bound by the MUFU (one ex2 per channel per pixel) and FP32 issue, not by
+// HBM (3.4 B/pixel algorithmic) -- see DESIGN.md.
 //
-// Work decomposition
-//   low-res "cell" (cy, cx) = the square between 4 neighbouring low-res nodes;
-//   every high-res pixel lies in exactly one cell (torch's i0 = min(floor(src), in-1)
-//   is re-expressed as cell = min(floor(src), in-2), lambda = clamp(src - cell, 0, 1),
+// Work decomposition (v2: warp-autonomous, no CTA barriers in the main loop)
+//   low-res "cell" (cy, cx) = the square between 4 neighbouring low-res nodes; every
+//   high-res pixel lies in exactly one cell (torch's i0 = min(floor(src), in-1) is
+//   re-expressed as cell = min(floor(src), in-2), lambda = clamp(src - cell, 0, 1),
 //   which gives identical values: for the last node lambda becomes exactly 1).
-//   CTA tile   = tcy x tcx cells; its (tcy+1) x (tcx+1) x CK low-res nodes are staged
-//                in shared memory, pre-multiplied by log2(e).
-//   work item  = one pixel row inside one cell (a "run" of ~8 pixels at 65x129 ->
-//                512x1024).  The vertical lerp is done ONCE per run, the horizontal
-//                lerp is one FFMA per pixel per channel:  t_k = a_k + lambda * d_k.
-//   LPR lanes share a run, each owning CPL channels (CK <= CPL*LPR).
-//   Backward: per run the horizontal transposed lerp is accumulated in registers,
-//   neighbouring runs are merged with one warp shuffle and written to a
-//   shared-memory [k][row][node] array; phase 2 applies the vertical transposed lerp
-//   and adds the tile's nodes into dLogits (red.global.add.f32 on tile borders).
-//   dT: per-thread register accumulators for the thread's current label column,
-//   flushed to a per-CTA shared tile when the label changes.
-//   Per-CTA partials (loss, count, dT) are reduced in a fixed order by a small
-//   finalize kernel, so loss / dT are run-to-run deterministic.
+//   unit       = UR cell-rows x CPW = 32/LPR cells, claimed dynamically by ONE WARP.
+//   lane group = LPR lanes own one cell; each lane owns CPL channels (CK <= CPL*LPR) and
+//                keeps the cell's 4 corner logits of its channels IN REGISTERS (pre-scaled
+//                by log2 e), so per pixel row the vertical lerp is 2 FFMA/channel and per
+//                pixel the horizontal lerp is ONE FFMA/channel:  t_k = a_k + lambda * d_k.
+//   Softmax uses a per-row upper bound M of the logits instead of the per-pixel max (the
+//   interpolant is a convex combination of the row's end points); a pixel whose exp-sum
+//   underflows (only with > 2^40 dynamic range inside one cell) is redone with the exact max.
+//   Backward: per pixel row the horizontal transposed lerp is accumulated in registers
+//   (Gs = sum g, G1 = sum lambda g), the left neighbour's G1 arrives by one warp shuffle, and
+//   the vertical transposed lerp is accumulated in registers too (Vt, Vb); per cell-row each
+//   lane group adds its two node rows to dLogits with red.global.add.f32 (coalesced across the
+//   warp); the unit's right edge column goes out the same way.
+//   dT: per-thread register accumulators D[] for the thread's current label column; flushed
+//   warp-collectively (shuffle tree, no atomics) into the warp's private fp64 shared tile
+//   when the label changes at a row boundary and at the end of every unit; a label change
+//   INSIDE a pixel run (rare on real label maps) takes a shared-memory atomic.
+//   Per-CTA partials (loss, count, dT; all fp64) are reduced in a fixed order by a small
+//   finalize kernel.  Units are claimed dynamically, so the grouping of the fp64 partial sums
+//   (and the order of the fp32 red.adds into dLogits, as in torch's own CUDA backward of
+//   upsample_bilinear2d) is not run-to-run deterministic in the last bit.
 #include "common.cuh"
 
 namespace simt {
@@ -48,13 +55,13 @@ struct HeadArgs {
   int B, CK, C, h, w, H, W, ignore;
   float sy, sx;    // torch's align_corners scales (float)(in-1)/(out-1)
   int ncy, ncx;    // number of cells = max(in-1, 1)
-  int tcy, tcx, tcx_log2;
-  int tiles_y, tiles_x;
-  long long ntiles;
-  int max_rows;
+  int ur;          // cell-rows per unit
+  int units_y, units_x;
+  long long nunits;
   float gscale;
   float* dlogits;
-  float* part_dT;       // [grid][C*CKP]
+  unsigned long long* counter;  // dynamic unit scheduler (zero on entry; finalize re-zeroes it)
+  double* part_dT;      // [grid][C*CKP]
   double* part_loss;    // [grid]
   long long* part_cnt;  // [grid]
   int* err;
@@ -90,28 +97,6 @@ __host__ __device__ inline int first_px_of_cell(int c, float scale, int ncell, i
   return X;
 }
 
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-struct SmemLayout {
-  size_t Ls, Ns, Es, Ts, dTs, rowlam, rowcell, xs, rs, red, total;
-};
-__host__ __device__ inline SmemLayout smem_layout(int CK, int CKP, int C, int tcy, int tcx, int max_rows, bool bwd) {
-  SmemLayout L;
-  size_t o = 0;
-  L.Ls = o;  o += align_up((size_t)CK * (tcy + 1) * (tcx + 1) * 4, 16);
-  L.Ns = o;  o += bwd ? align_up((size_t)CK * max_rows * tcx * 4, 16) : 0;
-  L.Es = o;  o += bwd ? align_up((size_t)CK * max_rows * 4, 16) : 0;
-  L.Ts = o;  o += align_up((size_t)C * CKP * 4, 16);
-  L.dTs = o; o += bwd ? align_up((size_t)C * CKP * 4, 16) : 0;
-  L.rowlam = o;  o += align_up((size_t)max_rows * 4, 16);
-  L.rowcell = o; o += align_up((size_t)max_rows * 4, 16);
-  L.xs = o;  o += align_up((size_t)(tcx + 1) * 4, 16);
-  L.rs = o;  o += align_up((size_t)(tcy + 2) * 4, 16);
-  L.red = o; o += 32 * 8 + 32 * 8;
-  L.total = o;
-  return L;
-}
-
 template <typename LabelT>
 __device__ __forceinline__ int load_label(const LabelT* p, long long idx);
 template <>
@@ -138,243 +123,313 @@ __device__ __forceinline__ float group_max(float v, unsigned gmask) {
   return v;
 }
 
+// Warp-collective flush of the per-thread dT accumulators D[] (column `old` of dT) into the
+// warp's PRIVATE fp64 shared tile wt[y][k].  Called with the whole warp converged.  Lanes with
+// the same label are summed with a shuffle tree and written by one lane per channel slice (plain
+// read-modify-write: nobody else touches this warp's tile) -- float/double atomicAdd on shared
+// memory is a CAS loop on sm_100 and collapses when a whole warp flushes the same hot class.
+// More than two distinct labels in one flush (incoherent label maps) fall back to the CAS path,
+// where the contention is spread over many addresses anyway.
+template <int CPL, int LPR>
+__device__ __forceinline__ void warp_flush_dT(float (&D)[CPL], int old, bool need, double* wt, int CKP, int CK,
+                                              int kbase, int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, need);
+#pragma unroll 1
+  for (int round = 0; m != 0u && round < 2; ++round) {
+    const int src = __ffs(m) - 1;
+    const int lab = __shfl_sync(0xffffffffu, old, src);
+    const bool mine = need && old == lab;
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    float tot[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      float v = mine ? D[j] : 0.f;
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      tot[j] = v;
+      if (mine) D[j] = 0.f;
+    }
+    if (lane < LPR) {  // lane `sub` writes its channel slice
+      double* dst = wt + lab * CKP + kbase;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        if (kbase + j < CK) dst[j] += (double)tot[j];
+    }
+    if (mine) need = false;
+    m &= ~grp;
+    __syncwarp();
+  }
+  if (need) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      if (kbase + j < CK) atomicAdd(&wt[old * CKP + kbase + j], (double)D[j]);
+      D[j] = 0.f;
+    }
+  }
+  __syncwarp();
+}
+
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   constexpr bool BWD = (MODE != MODE_FWD);
   constexpr int CKP = CPL * LPR;
+  constexpr int CPW = 32 / LPR;  // cells per warp unit
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CK = A.CK, C = A.C;
-  const int tcy = A.tcy, tcx = A.tcx;
-  const SmemLayout SL = smem_layout(CK, CKP, C, tcy, tcx, A.max_rows, BWD);
-  float* Ls = reinterpret_cast<float*>(smem_raw + SL.Ls);
-  float* Ns = reinterpret_cast<float*>(smem_raw + SL.Ns);
-  float* Es = reinterpret_cast<float*>(smem_raw + SL.Es);
-  float* Ts = reinterpret_cast<float*>(smem_raw + SL.Ts);
-  float* dTs = reinterpret_cast<float*>(smem_raw + SL.dTs);
-  float* rowlam = reinterpret_cast<float*>(smem_raw + SL.rowlam);
-  int* rowcell = reinterpret_cast<int*>(smem_raw + SL.rowcell);
-  int* xs = reinterpret_cast<int*>(smem_raw + SL.xs);
-  int* rs = reinterpret_cast<int*>(smem_raw + SL.rs);
-  double* red_d = reinterpret_cast<double*>(smem_raw + SL.red);
-  long long* red_i = reinterpret_cast<long long*>(smem_raw + SL.red + 32 * 8);
+  double* tiles = reinterpret_cast<double*>(smem_raw);                               // [NT/32][C*CKP] (BWD)
+  float* Ts = reinterpret_cast<float*>(smem_raw + (BWD ? (size_t)(NT / 32) * C * CKP * 8 : 0));  // [C][CKP]
+  __shared__ double red_d[NT / 32];
+  __shared__ long long red_i[NT / 32];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int sub = (LPR > 1) ? (tid & (LPR - 1)) : 0;
   const unsigned gmask = (LPR == 1) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
   const int kbase = sub * CPL;
+  const int pidx = lane / LPR;  // this lane group's cell within the unit
   const LabelT* labels = reinterpret_cast<const LabelT*>(A.labels);
-  const int pitchL = tcx + 1;
-  const int planeL = (tcy + 1) * pitchL;
+  const int h = A.h, w = A.w;
 
-  // ---- one-time per CTA: T transposed ([y][k], zero padded) and the dT tile ---------
+  // ---- one-time per CTA: T transposed ([y][k], zero padded) and the per-warp dT tiles ----
   for (int i = tid; i < C * CKP; i += NT) {
     int y = i / CKP, k = i - y * CKP;
     float v = 0.f;
     if (k < CK) v = A.T ? __ldg(A.T + (size_t)k * C + y) : (k == y ? 1.f : 0.f);
     Ts[i] = v;
-    if (BWD) dTs[i] = 0.f;
   }
+  if (BWD)
+    for (int i = tid; i < (NT / 32) * C * CKP; i += NT) tiles[i] = 0.0;
+  double* wt = tiles + (size_t)(tid >> 5) * C * CKP;
+  __syncthreads();
 
-  float D[CPL];  // dT accumulators for the thread's current label column
-  float Tc[CPL]; // T[:, cur] for this lane's channels
+  float D[CPL];   // dT accumulators for the thread's current label column
+  float Tc[CPL];  // T[:, cur] for this lane's channels
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { D[j] = 0.f; Tc[j] = 0.f; }
   int cur = -1;
-  float loss_acc = 0.f;  // sum of log2 q over this thread's valid pixels
-  int cnt = 0;
+  double loss_d = 0.0;  // sum of log2 q over this thread's valid pixels
+  long long cnt = 0;
   bool bad_label = false;
 
-  for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
-    const int tiles_per_img = A.tiles_y * A.tiles_x;
-    const int b = (int)(tile / tiles_per_img);
-    const int trem = (int)(tile - (long long)b * tiles_per_img);
-    const int tyi = trem / A.tiles_x, txi = trem - tyi * A.tiles_x;
-    const int cy0 = tyi * tcy, cx0 = txi * tcx;
-    const int ncy_t = min(tcy, A.ncy - cy0), ncx_t = min(tcx, A.ncx - cx0);
-    const int Y0 = first_px_of_cell(cy0, A.sy, A.ncy, A.H);
-    const int Y1 = first_px_of_cell(cy0 + ncy_t, A.sy, A.ncy, A.H);
-    const int rows = Y1 - Y0;
+  auto claim = [&]() -> long long {
+    unsigned long long u = 0;
+    if (lane == 0) u = atomicAdd(A.counter, 1ULL);
+    return (long long)__shfl_sync(0xffffffffu, u, 0);
+  };
 
-    __syncthreads();  // previous tile fully consumed (also orders the Ts/dTs init)
-    // ---- tile setup ---------------------------------------------------------------------
-    for (int i = tid; i <= tcx; i += NT)
-      xs[i] = first_px_of_cell(min(cx0 + i, cx0 + ncx_t), A.sx, A.ncx, A.W);
-    for (int i = tid; i <= tcy + 1; i += NT)
-      rs[i] = first_px_of_cell(min(cy0 + i, cy0 + ncy_t), A.sy, A.ncy, A.H) - Y0;
-    for (int r = tid; r < rows; r += NT) {
-      int cy = cell_of(Y0 + r, A.sy, A.ncy);
-      rowcell[r] = cy - cy0;
-      rowlam[r] = lambda_of(Y0 + r, A.sy, cy);
-    }
-    {
-      const float* src = A.logits + (size_t)b * CK * A.h * A.w;
-      const int nL = CK * planeL;
-      for (int i = tid; i < nL; i += NT) {
-        int k = i / planeL, rem = i - k * planeL;
-        int ty = rem / pitchL, tx = rem - ty * pitchL;
-        int gy = min(cy0 + ty, A.h - 1), gx = min(cx0 + tx, A.w - 1);
-        Ls[i] = __ldg(src + ((size_t)k * A.h + gy) * A.w + gx) * kLog2e;
-      }
-    }
-    __syncthreads();
+  long long unit = claim();
+  while (unit < A.nunits) {
+    const long long next_unit = claim();  // in flight while this unit is processed
+    const int per_img = A.units_y * A.units_x;
+    const int b = (int)(unit / per_img);
+    const int urem = (int)(unit - (long long)b * per_img);
+    const int uy = urem / A.units_x, ux = urem - uy * A.units_x;
+    const int cx = ux * CPW + pidx;
+    const bool cell_ok = cx < A.ncx;
+    const int xa = cell_ok ? first_px_of_cell(cx, A.sx, A.ncx, A.W) : 0;
+    const int xb = cell_ok ? first_px_of_cell(cx + 1, A.sx, A.ncx, A.W) : 0;
+    const bool last_cell = cell_ok && (pidx == CPW - 1 || cx == A.ncx - 1);
+    const int nrun = xb - xa;
+    const int nmax = __reduce_max_sync(0xffffffffu, nrun);
+    const int gx0 = min(cx, w - 1), gx1 = min(cx + 1, w - 1);
+    float loss_acc = 0.f;
 
-    // ---- phase 1: one run (row x cell) per LPR lanes -------------------------------------
-    const int nitems = rows << A.tcx_log2;
-    const int niter = (nitems * LPR + NT - 1) / NT;
-    for (int it = 0; it < niter; ++it) {
-      const int item = (it * NT + tid) / LPR;
-      const bool active = item < nitems;
-      const int r = item >> A.tcx_log2, cl = item & (tcx - 1);
-      float Gs[CPL], G1[CPL];
-      if (BWD) {
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) { Gs[j] = 0.f; G1[j] = 0.f; }
-      }
-      const int xa = active ? xs[cl] : 0, xb = active ? xs[cl + 1] : 0;
-      if (xb > xa) {
-        const int cyl = rowcell[r];
-        const float ly = rowlam[r];
-        const long long rowbase = ((long long)b * A.H + (Y0 + r)) * A.W;
-        // vertical lerp once per run; a = v0 - M, d = v1 - v0 (log2 domain)
-        float a[CPL], d[CPL];
-        float M = -INFINITY;
-        {
-          const float* L0 = Ls + cyl * pitchL + cl;
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            const int k = kbase + j;
-            if (k < CK) {
-              const float* Lk = L0 + k * planeL;
-              float l00 = Lk[0], l01 = Lk[1], l10 = Lk[pitchL], l11 = Lk[pitchL + 1];
-              float v0 = fmaf(ly, l10 - l00, l00);
-              float v1 = fmaf(ly, l11 - l01, l01);
-              a[j] = v0;
-              d[j] = v1 - v0;
-              M = fmaxf(M, fmaxf(v0, v1));
-            } else {
-              a[j] = -INFINITY;
-              d[j] = 0.f;
-            }
-          }
-        }
-        M = group_max<LPR>(M, gmask);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) a[j] -= M;
-
-        for (int X = xa; X < xb; ++X) {
-          const int y = load_label<LabelT>(labels, rowbase + X);
-          if (y == A.ignore || y < 0) continue;
-          if (y >= C) { bad_label = true; continue; }
-          if (y != cur) {
-            if (BWD && cur >= 0) {
-#pragma unroll
-              for (int j = 0; j < CPL; ++j) {
-                if (kbase + j < CK) atomicAdd(&dTs[cur * CKP + kbase + j], D[j]);
-                D[j] = 0.f;
-              }
-            }
-            cur = y;
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) Tc[j] = Ts[y * CKP + kbase + j];
-          }
-          const float lam = lambda_of(X, A.sx, cx0 + cl);
-          float e[CPL];
-          float sum = 0.f, s = 0.f;
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            e[j] = ex2_approx(fmaf(lam, d[j], a[j]));
-            sum += e[j];
-            s = fmaf(e[j], Tc[j], s);
-          }
-          sum = group_sum<LPR>(sum, gmask);
-          if (sum < 1e-12f) {
-            // the run-level bound M was far above this pixel's true max: redo with the exact max
-            float tm = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) tm = fmaxf(tm, fmaf(lam, d[j], a[j]));
-            tm = group_max<LPR>(tm, gmask);
-            sum = 0.f; s = 0.f;
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-              e[j] = ex2_approx(fmaf(lam, d[j], a[j]) - tm);
-              sum += e[j];
-              s = fmaf(e[j], Tc[j], s);
-            }
-            sum = group_sum<LPR>(sum, gmask);
-          }
-          s = group_sum<LPR>(s, gmask);
-          const float rsum = rcp_approx(sum);
-          if (MODE != MODE_BWD && sub == 0) loss_acc += lg2_approx(s * rsum);
-          cnt += (sub == 0);
-          if (BWD) {
-            const float is = rcp_approx(s);
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-              const float c = fmaf(-Tc[j], is, rsum);  // (p_k - p_k T_ky / q) / e_k
-              Gs[j] = fmaf(e[j], c, Gs[j]);
-              G1[j] = fmaf(lam * e[j], c, G1[j]);
-              D[j] = fmaf(e[j], is, D[j]);            // p_k / q
-            }
-          }
-        }
-      }
-      if (BWD) {
-        // node value for column cl of this row = G0(cl) + G1(cl-1); G1 of the previous run
-        // lives LPR lanes below (same warp because tcx*LPR divides 32).
-        __syncwarp();
+    const int cy_end = min(A.ncy, (uy + 1) * A.ur);
+    for (int cy = uy * A.ur; cy < cy_end; ++cy) {
+      const int Y0 = first_px_of_cell(cy, A.sy, A.ncy, A.H);
+      const int Y1 = first_px_of_cell(cy + 1, A.sy, A.ncy, A.H);
+      if (Y1 <= Y0) continue;  // warp-uniform
+      const int gy0 = min(cy, h - 1), gy1 = min(cy + 1, h - 1);
+      // ---- the cell's 4 corners for this lane's channels, in registers (log2 domain) ----
+      float l0[CPL], dl0[CPL], l1[CPL], dl1[CPL];
+      {
+        const float* src = A.logits + ((size_t)b * CK + kbase) * h * w;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-          float prev = __shfl_up_sync(0xffffffffu, G1[j], LPR);
-          if (cl == 0) prev = 0.f;
-          const int k = kbase + j;
-          if (active && k < CK) {
-            Ns[(k * A.max_rows + r) * tcx + cl] = (Gs[j] - G1[j]) + prev;
-            if (cl == tcx - 1) Es[k * A.max_rows + r] = G1[j];
+          float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+          if (cell_ok && kbase + j < CK) {
+            const float* p = src + (size_t)j * h * w;
+            c00 = __ldg(p + gy0 * w + gx0); c01 = __ldg(p + gy0 * w + gx1);
+            c10 = __ldg(p + gy1 * w + gx0); c11 = __ldg(p + gy1 * w + gx1);
+          }
+          l0[j] = c00 * kLog2e; dl0[j] = (c10 - c00) * kLog2e;
+          l1[j] = c01 * kLog2e; dl1[j] = (c11 - c01) * kLog2e;
+        }
+      }
+      float Vt[CPL], Vb[CPL];
+      if (BWD) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { Vt[j] = 0.f; Vb[j] = 0.f; }
+      }
+
+      for (int Y = Y0; Y < Y1; ++Y) {
+        const float ly = lambda_of(Y, A.sy, cy);
+        const long long rowbase = ((long long)b * A.H + Y) * A.W;
+        if (Y + 1 < Y1 && xb > xa)  // next row's labels on their way
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + rowbase + A.W + xa));
+        if (BWD) {
+          // Row boundary, warp converged: if the run's first valid label differs from the column
+          // the D[] accumulators belong to, flush them collectively before switching column.
+          int first_lab = -1;
+          for (int X = xa; X < xb; ++X) {
+            const int y = load_label<LabelT>(labels, rowbase + X);
+            if (y != A.ignore && y >= 0 && y < C) { first_lab = y; break; }
+          }
+          const bool sw = first_lab >= 0 && first_lab != cur;
+          const bool need = sw && cur >= 0;
+          if (__any_sync(0xffffffffu, need)) warp_flush_dT<CPL, LPR>(D, cur, need, wt, CKP, CK, kbase, lane);
+          if (sw) {
+            cur = first_lab;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) Tc[j] = Ts[cur * CKP + kbase + j];
+          }
+        }
+        float Gs[CPL], G1[CPL];
+        if (BWD) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) { Gs[j] = 0.f; G1[j] = 0.f; }
+        }
+        {
+          // vertical lerp once per row; a = v0 - M, d = v1 - v0
+          float a[CPL], d[CPL];
+          float M = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const float v0 = fmaf(ly, dl0[j], l0[j]);
+            const float v1 = fmaf(ly, dl1[j], l1[j]);
+            a[j] = v0;
+            d[j] = v1 - v0;
+            if (kbase + j < CK) M = fmaxf(M, fmaxf(v0, v1));
+          }
+          M = group_max<LPR>(M, 0xffffffffu);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) a[j] = (kbase + j < CK) ? a[j] - M : -INFINITY;
+
+          // The pixel loop is WARP-UNIFORM (nmax iterations, invalid lanes predicated off): the lane
+          // groups exchange partial sums with full-mask shuffles, which must not sit behind a
+          // divergent `continue` (group-masked shuffles serialise the 32/LPR groups).
+          for (int i = 0; i < nmax; ++i) {
+            const int X = xa + i;
+            const bool inb = i < nrun;
+            const int y = inb ? load_label<LabelT>(labels, rowbase + X) : A.ignore;
+            bool valid = inb && y != A.ignore && y >= 0;
+            if (valid && y >= C) { bad_label = true; valid = false; }
+            if (valid && y != cur) {
+              // label changed INSIDE a run (rare on coherent maps): per-lane flush
+              if (BWD && cur >= 0) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                  if (kbase + j < CK) atomicAdd(&wt[cur * CKP + kbase + j], (double)D[j]);
+                  D[j] = 0.f;
+                }
+              }
+              cur = y;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) Tc[j] = Ts[y * CKP + kbase + j];
+            }
+            const float lam = lambda_of(X, A.sx, cx);
+            float e[CPL];
+            float sum0 = 0.f, sum1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              e[j] = ex2_approx(fmaf(lam, d[j], a[j]));
+              if (j & 1) { sum1 += e[j]; s1 = fmaf(e[j], Tc[j], s1); }
+              else       { sum0 += e[j]; s0 = fmaf(e[j], Tc[j], s0); }
+            }
+            float sum = group_sum<LPR>(sum0 + sum1, 0xffffffffu);
+            float s = s0 + s1;
+            if (__any_sync(0xffffffffu, valid && sum < 1e-12f)) {
+              // the row-level bound M was far above some pixel's true max: redo with the exact max
+              float tm = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) tm = fmaxf(tm, fmaf(lam, d[j], a[j]));
+              tm = group_max<LPR>(tm, 0xffffffffu);
+              sum = 0.f; s = 0.f;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) {
+                e[j] = ex2_approx(fmaf(lam, d[j], a[j]) - tm);
+                sum += e[j];
+                s = fmaf(e[j], Tc[j], s);
+              }
+              sum = group_sum<LPR>(sum, 0xffffffffu);
+            }
+            s = group_sum<LPR>(s, 0xffffffffu);
+            const float rsum = valid ? rcp_approx(sum) : 0.f;
+            if (MODE != MODE_BWD && sub == 0 && valid) loss_acc += lg2_approx(s * rsum);
+            cnt += (sub == 0 && valid);
+            if (BWD) {
+              const float is = valid ? rcp_approx(s) : 0.f;
+              const float lis = lam * is, lrs = lam * rsum;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) {
+                const float c = fmaf(-Tc[j], is, rsum);     // (p_k - p_k T_ky / q) / e_k
+                const float c1 = fmaf(-Tc[j], lis, lrs);    // lambda * c
+                Gs[j] = fmaf(e[j], c, Gs[j]);
+                G1[j] = fmaf(e[j], c1, G1[j]);
+                D[j] = fmaf(e[j], is, D[j]);                // p_k / q
+              }
+            }
+          }
+        }
+        if (BWD) {
+          // node column cx of this row = G0(cx) + G1(cx-1); the left neighbour is LPR lanes below
+          __syncwarp();
+          const float wy1 = ly, wy0 = 1.f - ly;
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            float prev = __shfl_up_sync(0xffffffffu, G1[j], LPR);
+            if (pidx == 0) prev = 0.f;
+            const float n = (Gs[j] - G1[j]) + prev;
+            Vt[j] = fmaf(wy0, n, Vt[j]);
+            Vb[j] = fmaf(wy1, n, Vb[j]);
+          }
+          if (last_cell) {
+            // right edge of the unit: node column cx+1 belongs to the next unit (or is the image's
+            // last column); add this row's share directly
+            float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
+            const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              if (kbase + j < CK) {
+                float* pk = dst + (size_t)j * h * w;
+                atomicAdd(pk + gy0 * w + gx1, wy0 * G1[j] * gs);
+                atomicAdd(pk + gy1 * w + gx1, wy1 * G1[j] * gs);
+              }
+            }
+          }
+        }
+      }  // rows of the cell-row
+
+      if (BWD && cell_ok) {
+        float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
+        const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          if (kbase + j < CK) {
+            float* pk = dst + (size_t)j * h * w;
+            atomicAdd(pk + gy0 * w + gx0, Vt[j] * gs);
+            atomicAdd(pk + gy1 * w + gx0, Vb[j] * gs);
           }
         }
       }
-    }
+    }  // cell-rows of the unit
 
+    // per-unit hand-off: fp32 partials of a unit are summed in a fixed order; across units in fp64
     if (BWD) {
-      __syncthreads();
-      // ---- phase 2: vertical transposed lerp, one thread per (k, node row, node col) -----
-      const int nny = ncy_t + 1, nnx = ncx_t + 1;
-      const int nnodes = CK * nny * nnx;
-      float* dst = A.dlogits + (size_t)b * CK * A.h * A.w;
-      for (int i = tid; i < nnodes; i += NT) {
-        const int k = i / (nny * nnx);
-        const int rem = i - k * (nny * nnx);
-        const int ty = rem / nnx, tx = rem - ty * nnx;
-        const float* col = (tx < tcx) ? (Ns + (size_t)k * A.max_rows * tcx + tx) : (Es + (size_t)k * A.max_rows);
-        const int cstride = (tx < tcx) ? tcx : 1;
-        float acc = 0.f;
-        if (ty >= 1)
-          for (int r = rs[ty - 1]; r < rs[ty]; ++r) acc = fmaf(rowlam[r], col[r * cstride], acc);
-        if (ty < ncy_t)
-          for (int r = rs[ty]; r < rs[ty + 1]; ++r) acc = fmaf(1.f - rowlam[r], col[r * cstride], acc);
-        if (MODE == MODE_BWD) acc *= A.gscale;
-        const int gy = min(cy0 + ty, A.h - 1), gx = min(cx0 + tx, A.w - 1);
-        atomicAdd(dst + ((size_t)k * A.h + gy) * A.w + gx, acc);
-      }
+      warp_flush_dT<CPL, LPR>(D, cur, cur >= 0, wt, CKP, CK, kbase, lane);
     }
+    loss_d += (double)loss_acc;
+    unit = next_unit;
   }
 
   // ---- CTA epilogue: partials ---------------------------------------------------------------
-  if (BWD && cur >= 0) {
-#pragma unroll
-    for (int j = 0; j < CPL; ++j)
-      if (kbase + j < CK) atomicAdd(&dTs[cur * CKP + kbase + j], D[j]);
-  }
   if (bad_label) atomicOr(A.err, SIMT_ERRBIT_LABEL_RANGE);
-  double dl = (double)loss_acc;
-  long long dc = cnt;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    dl += __shfl_xor_sync(0xffffffffu, dl, o);
-    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+    loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if (lane == 0) { red_d[tid >> 5] = dl; red_i[tid >> 5] = dc; }
+  if (lane == 0) { red_d[tid >> 5] = loss_d; red_i[tid >> 5] = cnt; }
   __syncthreads();
   if (tid == 0) {
     double tl = 0; long long tc = 0;
@@ -383,16 +438,21 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     A.part_cnt[blockIdx.x] = tc;
   }
   if (BWD) {
-    float* pd = A.part_dT + (size_t)blockIdx.x * C * CKP;
-    for (int i = tid; i < C * CKP; i += NT) pd[i] = dTs[i];
+    double* pd = A.part_dT + (size_t)blockIdx.x * C * CKP;
+    for (int i = tid; i < C * CKP; i += NT) {
+      double v = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NT / 32; ++wv) v += tiles[(size_t)wv * C * CKP + i];
+      pd[i] = v;
+    }
   }
 }
 
 // One warp per output: outputs 0 .. C*CKP-1 are dT entries ([y][k] layout of the partials),
-// then loss and count.  Fixed summation order => deterministic.
+// then loss and count.  Fixed summation order over the CTA partials.
 __global__ void __launch_bounds__(256) head_finalize_kernel(
-    const float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
-    int nparts, int CK, int CKP, int C, int mode, float gscale,
+    const double* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
+    int nparts, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
     double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -402,7 +462,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(
     if (k >= CK) return;
     double s = 0;
     if (mode != MODE_FWD)
-      for (int g = lane; g < nparts; g += 32) s += (double)part_dT[(size_t)g * ndt + warp];
+      for (int g = lane; g < nparts; g += 32) s += part_dT[(size_t)g * ndt + warp];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
@@ -418,6 +478,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(
       c += __shfl_xor_sync(0xffffffffu, c, o);
     }
     if (lane == 0) {
+      *counter = 0ULL;  // the main kernel of this call has finished: re-arm the unit scheduler
       const double ls = -kLn2 * l;
       if (stats) { stats[0] = ls; stats[1] = (double)c; }
       if (loss_mean) {
@@ -449,49 +510,43 @@ __global__ void head_scale_kernel(float* __restrict__ dlogits, long long n, cons
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// workspace: [part_loss f64 x G][part_cnt i64 x G][part_dT f32 x G*C*CKPmax], G = max grid
+// workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f64 x G*C*CKPmax]
 static constexpr int kMaxGridPerSm = 8;
 static constexpr int kMaxCKP = 64;
 
-struct Tuning { int tcy, tcx, threads, lpr; };
+struct Tuning { int ur, unused, threads, lpr; };
 static Tuning g_tuning = {0, 0, 0, 0};
 
 struct Plan {
-  int CPL, LPR, NT, MINB;
-  int tcy, tcx, tcx_log2, tiles_y, tiles_x, max_rows;
-  long long ntiles;
-  int CKP;
+  int CPL, LPR, NT, MINB, CKP;
   size_t smem;
-  int grid;
 };
 
-static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
-
-static int max_rows_for(int tcy, int ncy, float sy, int H) {
-  int mr = 1;
-  for (int cy0 = 0; cy0 < ncy; cy0 += tcy) {
-    int n = (tcy < ncy - cy0) ? tcy : (ncy - cy0);
-    int r = first_px_of_cell(cy0 + n, sy, ncy, H) - first_px_of_cell(cy0, sy, ncy, H);
-    if (r > mr) mr = r;
-  }
-  return mr;
-}
-
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB>
-static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out, bool query_only) {
+static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
   auto kern = head_kernel<CPL, LPR, MODE, LabelT, NT, MINB>;
-  SIMT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-  int occ = 0;
-  SIMT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, P.smem));
+  // per-instantiation cache of the attribute / occupancy queries (keyed by device and smem size)
+  static int c_dev = -1, c_occ = 0;
+  static size_t c_smem = 0;
+  int dev = 0;
+  SIMT_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != c_dev || P.smem != c_smem) {
+    SIMT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    SIMT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, kern, NT, P.smem));
+    c_dev = dev;
+    c_smem = P.smem;
+  }
+  const int occ = c_occ;
   if (occ < 1) return SIMT_ENOSMEM;
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   long long g = (long long)occ * di.sm_count;
   if (g > (long long)di.sm_count * kMaxGridPerSm) g = (long long)di.sm_count * kMaxGridPerSm;
-  if (g > A.ntiles) g = A.ntiles;
+  const long long need = (A.nunits + NT / 32 - 1) / (NT / 32);
+  if (g > need) g = need;
+  if (g < 1) g = 1;
   *grid_out = (int)g;
-  if (query_only) return 0;
   prof_begin(st);
   kern<<<(int)g, NT, P.smem, st>>>(A);
   prof_end(st);
@@ -500,31 +555,29 @@ static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* gr
 
 // channel-count -> (CPL, LPR, threads, min CTAs/SM) instantiations
 #define SIMT_HEAD_CONFIGS(X) \
-  X(19, 1, 128, 3)           \
-  X(10, 2, 256, 2)           \
-  X(12, 2, 256, 2)           \
-  X(17, 2, 128, 3)           \
-  X(16, 4, 128, 3)
+  X(10, 2, 128, 3)           \
+  X(6, 4, 128, 4)            \
+  X(9, 4, 128, 3)            \
+  X(16, 4, 128, 2)
 
 template <int MODE, typename LabelT>
-static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out, bool query_only) {
+static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
 #define X(cpl, lpr, nt, minb) \
-  if (P.CPL == cpl && P.LPR == lpr) return launch_cfg<cpl, lpr, MODE, LabelT, nt, minb>(A, P, st, grid_out, query_only);
+  if (P.CPL == cpl && P.LPR == lpr) return launch_cfg<cpl, lpr, MODE, LabelT, nt, minb>(A, P, st, grid_out);
   SIMT_HEAD_CONFIGS(X)
 #undef X
   return SIMT_EUNSUPPORTED;
 }
 
-static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out,
-                        bool query_only) {
+static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
   if (label_bytes == 1) {
-    if (mode == MODE_FWD) return dispatch<MODE_FWD, uint8_t>(A, P, st, grid_out, query_only);
-    if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, uint8_t>(A, P, st, grid_out, query_only);
-    return dispatch<MODE_BWD, uint8_t>(A, P, st, grid_out, query_only);
+    if (mode == MODE_FWD) return dispatch<MODE_FWD, uint8_t>(A, P, st, grid_out);
+    if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, uint8_t>(A, P, st, grid_out);
+    return dispatch<MODE_BWD, uint8_t>(A, P, st, grid_out);
   }
-  if (mode == MODE_FWD) return dispatch<MODE_FWD, long long>(A, P, st, grid_out, query_only);
-  if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, long long>(A, P, st, grid_out, query_only);
-  return dispatch<MODE_BWD, long long>(A, P, st, grid_out, query_only);
+  if (mode == MODE_FWD) return dispatch<MODE_FWD, long long>(A, P, st, grid_out);
+  if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, long long>(A, P, st, grid_out);
+  return dispatch<MODE_BWD, long long>(A, P, st, grid_out);
 }
 
 static int choose_config(int CK, int lpr_req, Plan* P) {
@@ -538,9 +591,10 @@ static int choose_config(int CK, int lpr_req, Plan* P) {
   for (const Cfg& c : cfgs) {
     if (c.cpl * c.lpr < CK) continue;
     if (lpr_req > 0 && c.lpr != lpr_req) continue;
-    // prefer the fewest lanes per run, then the least channel padding
+    // prefer the fewest lanes per cell, then the least channel padding
     if (!best || c.lpr < best->lpr || (c.lpr == best->lpr && c.cpl * c.lpr < best->cpl * best->lpr)) best = &c;
   }
+  if (!best && lpr_req > 0) return choose_config(CK, 0, P);
   if (!best) return SIMT_EUNSUPPORTED;
   P->CPL = best->cpl; P->LPR = best->lpr; P->NT = best->nt; P->MINB = best->minb;
   P->CKP = best->cpl * best->lpr;
@@ -550,53 +604,27 @@ static int choose_config(int CK, int lpr_req, Plan* P) {
 static int make_plan(int mode, int B, int CK, int C, int h, int w, int H, int W, HeadArgs* A, Plan* P) {
   int rc = choose_config(CK, g_tuning.lpr, P);
   if (rc) return rc;
-  DeviceInfo di;
-  rc = device_info(&di);
-  if (rc) return rc;
   A->sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   A->sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
   A->ncy = h > 1 ? h - 1 : 1;
   A->ncx = w > 1 ? w - 1 : 1;
-  const int max_tcx = 32 / P->LPR;
-  int tcx = g_tuning.tcx > 0 ? g_tuning.tcx : 8;
-  int tcy = g_tuning.tcy > 0 ? g_tuning.tcy : 8;
-  if (tcx > max_tcx) tcx = max_tcx;
-  tcx = 1 << ilog2(tcx);
-  if (tcx > max_tcx) tcx = max_tcx;
+  // cell-rows per unit: ~8 pixel rows per unit keeps the per-unit overhead amortised
+  int ur = g_tuning.ur;
+  if (ur <= 0) {
+    const double rows_per_cell = (double)H / (double)A->ncy;
+    ur = (int)(8.0 / rows_per_cell + 0.5);
+    if (ur < 1) ur = 1;
+    if (ur > 32) ur = 32;
+  }
+  const int cpw = 32 / P->LPR;
+  A->ur = ur;
+  A->units_y = (A->ncy + ur - 1) / ur;
+  A->units_x = (A->ncx + cpw - 1) / cpw;
+  A->nunits = (long long)B * A->units_y * A->units_x;
   const bool bwd = mode != MODE_FWD;
-  auto ntiles_of = [&](int ty, int tx) {
-    return (long long)B * ((A->ncy + ty - 1) / ty) * ((A->ncx + tx - 1) / tx);
-  };
-  if (g_tuning.tcx <= 0 && g_tuning.tcy <= 0) {
-    // enough tiles to balance a persistent grid of ~3 CTAs/SM: shrink small problems' tiles
-    const long long want = 4LL * 3 * di.sm_count;
-    while (ntiles_of(tcy, tcx) < want && (tcy > 2 || tcx > 4)) {
-      if (tcy >= tcx && tcy > 2) tcy >>= 1; else if (tcx > 4) tcx >>= 1; else tcy >>= 1;
-    }
-  }
-  // shrink until the tile fits in shared memory
-  for (;;) {
-    int mr = max_rows_for(tcy, A->ncy, A->sy, H);
-    SmemLayout SL = smem_layout(CK, P->CKP, C, tcy, tcx, mr, bwd);
-    const size_t budget = ((size_t)228 * 1024 - (size_t)P->MINB * 1024) / P->MINB;  // MINB CTAs per SM
-    if (SL.total <= budget || (tcy == 1 && tcx == 1)) {
-      if (SL.total > (size_t)di.smem_optin) return SIMT_ENOSMEM;
-      P->max_rows = mr;
-      P->smem = SL.total;
-      break;
-    }
-    if (tcy > 1) tcy >>= 1; else tcx >>= 1;
-  }
-  P->tcy = tcy; P->tcx = tcx; P->tcx_log2 = ilog2(tcx);
-  P->tiles_y = (A->ncy + tcy - 1) / tcy;
-  P->tiles_x = (A->ncx + tcx - 1) / tcx;
-  P->ntiles = (long long)B * P->tiles_y * P->tiles_x;
-  A->tcy = tcy; A->tcx = tcx; A->tcx_log2 = P->tcx_log2;
-  A->tiles_y = P->tiles_y; A->tiles_x = P->tiles_x; A->ntiles = P->ntiles;
-  A->max_rows = P->max_rows;
+  P->smem = (bwd ? (size_t)(P->NT / 32) * C * P->CKP * 8 : 0) + (size_t)C * P->CKP * 4;
   return 0;
 }
-
 
 static int validate(const float* logits, int B, int CK, int h, int w, int C, const void* labels, int label_bytes,
                     int H, int W, const float* T) {
@@ -629,18 +657,19 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   if (rc) return rc;
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  A.part_loss = reinterpret_cast<double*>(ws);
-  A.part_cnt = reinterpret_cast<long long*>(ws + G * 8);
-  A.part_dT = reinterpret_cast<float*>(ws + G * 16);
+  A.counter = reinterpret_cast<unsigned long long*>(ws);
+  A.part_loss = reinterpret_cast<double*>(ws + 64);
+  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
+  A.part_dT = reinterpret_cast<double*>(ws + 64 + G * 16);
   if (mode != MODE_FWD)
     SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
   int grid = 0;
-  rc = dispatch_all(mode, label_bytes, A, P, st, &grid, false);
+  rc = dispatch_all(mode, label_bytes, A, P, st, &grid);
   if (rc) return rc;
   const int nwarps = C * P.CKP + 1;
   const int fgrid = (nwarps * 32 + 255) / 256;
   head_finalize_kernel<<<fgrid, 256, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, mode, gscale,
-                                              stats, loss_mean, dT_out, err_flag);
+                                              A.counter, stats, loss_mean, dT_out, err_flag);
   return (int)cudaGetLastError();
 }
 
@@ -655,10 +684,12 @@ size_t simt_head_workspace_bytes(int B, int CK, int C, int h, int w, int H, int 
   DeviceInfo di;
   if (device_info(&di)) di.sm_count = 256;
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
-  return G * 16 + G * (size_t)(C > 0 ? C : 1) * kMaxCKP * sizeof(float);
+  return 64 + G * 16 + G * (size_t)(C > 0 ? C : 1) * kMaxCKP * sizeof(double);
 }
 
-void simt_head_set_tuning(int tcy, int tcx, int threads, int lpr) { g_tuning = {tcy, tcx, threads, lpr}; }
+void simt_head_set_tuning(int cell_rows_per_unit, int reserved, int threads, int lpr) {
+  g_tuning = {cell_rows_per_unit, reserved, threads, lpr};
+}
 
 int simt_head_fwd(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
                   int label_bytes, int H, int W, int ignore, double* stats, float* loss_mean, int* err_flag,

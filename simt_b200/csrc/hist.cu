@@ -265,6 +265,7 @@ static constexpr long long kMaxPerLaunch = 1LL << 31;  // keeps the u32 CTA hist
 
 static int run_hist(const void* a, int a_bytes, const void* b, int b_bytes, long long n, const uint8_t* lut,
                     int n_rows, int n_cols, long long* hist, int* err_flag, cudaStream_t st) {
+  if (n == 0) return 0;
   if (!a || !hist || n < 0 || n_rows <= 0 || n_cols <= 0) return SIMT_EINVAL;
   if ((a_bytes != 1 && a_bytes != 8) || (b && b_bytes != 1 && b_bytes != 8)) return SIMT_EINVAL;
   if (lut && a_bytes != 1) return SIMT_EINVAL;
@@ -342,7 +343,7 @@ void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll) { g_hist_tuni
 
 int simt_confusion(const void* a, int a_bytes, const void* b, int b_bytes, long long n, const uint8_t* lut256,
                    int n_rows, int n_cols, long long* hist, int* err_flag, void* stream) {
-  if (!b) return SIMT_EINVAL;
+  if (!b && n != 0) return SIMT_EINVAL;
   return run_hist(a, a_bytes, b, b_bytes, n, lut256, n_rows, n_cols, hist, err_flag, (cudaStream_t)stream);
 }
 

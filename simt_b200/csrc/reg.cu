@@ -1,0 +1,255 @@
+// T regularisers and anchor statistics of the SimT head (sm_100a).
+//
+// simt_t_regularizers: convex + volume terms of one head and their gradients in ONE single-CTA
+// launch.  Replaces, per head, tools/trainV2_simt.py:412-415 (W.mm(T), MSELoss(sum)), :417-421
+// (T^T T, torch.linalg.det -> cuSOLVER LU, log sqrt abs, and the host sync at torch.isinf) and the
+// autograd backward of those lines:  ~11 tiny launches + a device->host sync become one launch.
+//   convex = -||W T||_F^2            d/dT = -2 W^T (W T)      d/dW = -2 (W T) T^T
+//   volume = 0.5 log|det(T^T T)|     d/dT = T (T^T T)^-1      (0 and zero gradient if not finite)
+// G = T^T T is symmetric positive (semi-)definite, so |det| = det and a Cholesky factorisation
+// in fp64 gives log det = 2 sum log L_ii and G^-1 by two triangular solves.
+//
+// simt_anchor_stats: Anchor_index / Exist_label of trainV2_simt.py:375-377 computed from the
+// LOW-res logits (the [N, CK] upsampled tensor is never materialised): per channel the arg-max
+// pixel of the bilinearly upsampled logit, and the set of classes that are the per-pixel arg-max
+// somewhere.  Ties: the smallest pixel index / smallest class wins (torch's CPU argmax).
+#include "common.cuh"
+
+namespace simt {
+
+static constexpr int kMaxC = 64;  // C and CK bound for the single-CTA regulariser kernel
+
+__global__ void __launch_bounds__(256) t_reg_kernel(const float* __restrict__ T, const float* __restrict__ W, int CK,
+                                                     int C, float* __restrict__ out2, float* __restrict__ dT_convex,
+                                                     float* __restrict__ dT_volume, float* __restrict__ dW_convex) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // doubles first (alignment), then floats
+  double* G = reinterpret_cast<double*>(smem_raw);          // [C][C]  T^T T, then its Cholesky factor L
+  double* X = G + C * C;                                     // [C][CK] G^-1 T^T
+  float* Ts = reinterpret_cast<float*>(X + C * CK);          // [CK][C]
+  float* Ws = Ts + CK * C;                                   // [CK][CK]
+  float* P = Ws + CK * CK;                                   // [CK][C]  W T
+  __shared__ double red[8];
+  __shared__ int spd_ok;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < CK * C; i += nt) Ts[i] = T[i];
+  if (W)
+    for (int i = tid; i < CK * CK; i += nt) Ws[i] = W[i];
+  if (tid == 0) spd_ok = 1;
+  __syncthreads();
+
+  // ---- convex: P = W T, loss = -sum P^2 --------------------------------------------------------
+  double part = 0;
+  if (W) {
+    for (int i = tid; i < CK * C; i += nt) {
+      const int r = i / C, c = i - r * C;
+      float acc = 0.f;
+      for (int k = 0; k < CK; ++k) acc = fmaf(Ws[r * CK + k], Ts[k * C + c], acc);
+      P[i] = acc;
+      part += (double)acc * (double)acc;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  // ---- G = T^T T (fp64 accumulate) ---------------------------------------------------------------
+  for (int i = tid; i < C * C; i += nt) {
+    const int a = i / C, b = i - a * C;
+    double acc = 0;
+    for (int k = 0; k < CK; ++k) acc += (double)Ts[k * C + a] * (double)Ts[k * C + b];
+    G[i] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int k = 0; k < nt / 32; ++k) s += red[k];
+    out2[0] = W ? (float)(-s) : 0.f;
+  }
+  if (W) {
+    // dT_convex = -2 W^T P ; dW_convex = -2 P T^T
+    for (int i = tid; i < CK * C; i += nt) {
+      const int r = i / C, c = i - r * C;
+      float acc = 0.f;
+      for (int k = 0; k < CK; ++k) acc = fmaf(Ws[k * CK + r], P[k * C + c], acc);
+      dT_convex[i] = -2.f * acc;
+    }
+    for (int i = tid; i < CK * CK; i += nt) {
+      const int r = i / CK, c = i - r * CK;
+      float acc = 0.f;
+      for (int k = 0; k < C; ++k) acc = fmaf(P[r * C + k], Ts[c * C + k], acc);
+      dW_convex[i] = -2.f * acc;
+    }
+  }
+
+  // ---- Cholesky G = L L^T in place (lower), column by column -----------------------------------------
+  for (int j = 0; j < C; ++j) {
+    __syncthreads();
+    if (tid == 0) {
+      double d = G[j * C + j];
+      for (int k = 0; k < j; ++k) d -= G[j * C + k] * G[j * C + k];
+      if (!(d > 0.0) || !isfinite(d)) { spd_ok = 0; d = 1.0; }
+      G[j * C + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double ljj = G[j * C + j];
+    for (int i = j + 1 + tid; i < C; i += nt) {
+      double v = G[i * C + j];
+      for (int k = 0; k < j; ++k) v -= G[i * C + k] * G[j * C + k];
+      G[i * C + j] = v / ljj;
+    }
+  }
+  __syncthreads();
+  double logdet = 0;
+  if (tid == 0) {
+    for (int j = 0; j < C; ++j) logdet += log(G[j * C + j]);
+    const double vol = logdet;  // 0.5 * log det(G) = 0.5 * 2 * sum log L_jj
+    const bool fin = spd_ok && isfinite(vol);
+    if (!fin) spd_ok = 0;
+    out2[1] = fin ? (float)vol : 0.f;  // trainV2_simt.py:420-421
+  }
+  __syncthreads();
+  // ---- X = G^-1 T^T: one thread per right-hand side (a row of T) -----------------------------------------
+  for (int r = tid; r < CK; r += nt) {
+    // forward: L y = t ; backward: L^T x = y ; X[:, r]
+    for (int i = 0; i < C; ++i) {
+      double v = (double)Ts[r * C + i];
+      for (int k = 0; k < i; ++k) v -= G[i * C + k] * X[k * CK + r];
+      X[i * CK + r] = v / G[i * C + i];
+    }
+    for (int i = C - 1; i >= 0; --i) {
+      double v = X[i * CK + r];
+      for (int k = i + 1; k < C; ++k) v -= G[k * C + i] * X[k * CK + r];
+      X[i * CK + r] = v / G[i * C + i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < CK * C; i += nt) {
+    const int r = i / C, c = i - r * C;
+    dT_volume[i] = spd_ok ? (float)X[c * CK + r] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// anchor statistics
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_max(float v, long long idx) {
+  // monotone float -> uint, high 32 bits; low 32 bits = ~idx so that the SMALLEST index wins ties
+  unsigned u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
+}
+
+template <int MAXCK>
+__global__ void __launch_bounds__(256) anchor_stats_kernel(const float* __restrict__ logits, int B, int CK, int h,
+                                                            int w, int H, int W, float sy, float sx,
+                                                            unsigned long long* __restrict__ packed /*[CK]*/,
+                                                            unsigned long long* __restrict__ exist) {
+  // one thread per output pixel (grid-stride); values follow torch's formula
+  //   w0h*(w0w*x00 + w1w*x01) + w1h*(w0w*x10 + w1w*x11)
+  __shared__ unsigned long long s_best[MAXCK];
+  __shared__ unsigned long long s_exist;
+  for (int k = threadIdx.x; k < CK; k += blockDim.x) s_best[k] = 0ull;
+  if (threadIdx.x == 0) s_exist = 0ull;
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long my_exist = 0ull;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const int X = (int)(p % W);
+    const long long t = p / W;
+    const int Y = (int)(t % H);
+    const int b = (int)(t / H);
+    const float fy = __fmul_rn(sy, (float)Y), fx = __fmul_rn(sx, (float)X);
+    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+    const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* base = logits + (size_t)b * CK * h * w;
+    float best = -INFINITY;
+    int bestk = 0;
+    for (int k = 0; k < CK; ++k) {
+      const float* pl = base + (size_t)k * h * w;
+      const float v00 = __ldg(pl + y0 * w + x0), v01 = __ldg(pl + y0 * w + x1);
+      const float v10 = __ldg(pl + y1 * w + x0), v11 = __ldg(pl + y1 * w + x1);
+      const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+      const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+      const float z = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+      if (z > best) { best = z; bestk = k; }
+      // per-channel arg-max over pixels: warp-aggregate, then one shared atomicMax per warp
+      unsigned long long pk = pack_max(z, p);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(__activemask(), pk, o);
+        pk = other > pk ? other : pk;
+      }
+      if ((threadIdx.x & 31) == 0 || true) {
+        if (pk > s_best[k] && pack_max(z, p) == pk) atomicMax(&s_best[k], pk);
+      }
+    }
+    my_exist |= 1ull << bestk;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_exist |= __shfl_xor_sync(0xffffffffu, my_exist, o);
+  if ((threadIdx.x & 31) == 0) atomicOr(&s_exist, my_exist);
+  __syncthreads();
+  for (int k = threadIdx.x; k < CK; k += blockDim.x)
+    if (s_best[k]) atomicMax(&packed[k], s_best[k]);
+  if (threadIdx.x == 0 && s_exist) atomicOr(exist, s_exist);
+}
+
+__global__ void anchor_unpack_kernel(const unsigned long long* __restrict__ packed, int CK,
+                                     long long* __restrict__ anchor_idx, float* __restrict__ anchor_val) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= CK) return;
+  const unsigned long long pk = packed[k];
+  anchor_idx[k] = (long long)(0xffffffffu - (unsigned)(pk & 0xffffffffull));
+  unsigned u = (unsigned)(pk >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  if (anchor_val) anchor_val[k] = __uint_as_float(u);
+}
+
+}  // namespace simt
+
+using namespace simt;
+
+extern "C" {
+
+int simt_t_regularizers(const float* T, const float* W, int CK, int C, float* out2, float* dT_convex,
+                        float* dT_volume, float* dW_convex, void* stream) {
+  if (!T || !out2 || !dT_volume || CK <= 0 || C <= 0) return SIMT_EINVAL;
+  if (W && (!dT_convex || !dW_convex)) return SIMT_EINVAL;
+  if (CK > kMaxC || C > kMaxC || C > CK) return SIMT_EUNSUPPORTED;
+  const size_t smem = (size_t)(C * C + C * CK) * 8 + (size_t)(2 * CK * C + CK * CK) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SIMT_CUDA_TRY(cudaFuncSetAttribute(t_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  t_reg_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(T, W, CK, C, out2, dT_convex, dT_volume, dW_convex);
+  return (int)cudaGetLastError();
+}
+
+int simt_anchor_stats(const float* logits, int B, int CK, int h, int w, int H, int W, long long* anchor_idx,
+                      float* anchor_val, unsigned long long* exist_mask, unsigned long long* scratch, void* stream) {
+  if (!logits || !anchor_idx || !exist_mask || !scratch) return SIMT_EINVAL;
+  if (B <= 0 || CK <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SIMT_EINVAL;
+  if (CK > 64) return SIMT_EUNSUPPORTED;
+  if ((long long)B * H * W > 0xffffffffLL) return SIMT_EUNSUPPORTED;  // pixel index is packed in 32 bits
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  SIMT_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * CK, st));
+  SIMT_CUDA_TRY(cudaMemsetAsync(exist_mask, 0, sizeof(unsigned long long), st));
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  long long grid = ((long long)B * H * W + 255) / 256;
+  if (grid > (long long)di.sm_count * 8) grid = (long long)di.sm_count * 8;
+  anchor_stats_kernel<64><<<(int)grid, 256, 0, st>>>(logits, B, CK, h, w, H, W, sy, sx, scratch, exist_mask);
+  SIMT_CUDA_TRY(cudaGetLastError());
+  anchor_unpack_kernel<<<1, 64, 0, st>>>(scratch, CK, anchor_idx, anchor_val);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

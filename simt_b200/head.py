@@ -192,3 +192,60 @@ class SimTHead(torch.nn.Module):
 
     def forward(self, logits_lo, T, labels):
         return simt_head(logits_lo, T, labels, self.out_size, self.ignore_label, self.group)
+
+
+class HeadRunner:
+    """Static-shape, allocation-free form of the fused head for training loops and benchmarks.
+
+    All outputs are preallocated once; ``step`` enqueues memset + fused fwd/bwd kernel + finalize
+    [+ one all-reduce of the 2.9 KB stats buffer when ``group`` is given] + scale kernel, and
+    returns views (loss f32[], dlogits f32[B,CK,h,w], dT f32[CK,C]) without synchronising.
+    """
+
+    def __init__(self, B, CK, C, h, w, H, W, device=None, ignore=255, label_dtype=torch.uint8, group=None):
+        self.lib = _lib.load()
+        self.shape = (int(B), int(CK), int(C), int(h), int(w), int(H), int(W))
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ignore = int(ignore)
+        self.label_bytes = 1 if label_dtype == torch.uint8 else 8
+        self.group = group
+        B, CK, C, h, w, H, W = self.shape
+        self.ws = torch.zeros(self.lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W), dtype=torch.uint8, device=self.dev)
+        self.stats = torch.zeros(2 + CK * C, dtype=torch.float64, device=self.dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.dlogits = torch.zeros(B, CK, h, w, dtype=torch.float32, device=self.dev)
+        self.dT = torch.zeros(CK, C, dtype=torch.float32, device=self.dev)
+        self.err = error_flag(self.dev)
+        self._p = (self.ws.data_ptr(), self.ws.numel(), self.stats.data_ptr(), self.loss.data_ptr(),
+                   self.dlogits.data_ptr(), self.dT.data_ptr(), self.err.data_ptr())
+
+    def fwdbwd(self, logits, T, labels, stream=None):
+        B, CK, C, h, w, H, W = self.shape
+        ws, nws, stats, loss, dl, _, err = self._p
+        rc = self.lib.simt_head_fwdbwd(logits.data_ptr(), B, CK, h, w, None if T is None else T.data_ptr(), C,
+                                       labels.data_ptr(), self.label_bytes, H, W, self.ignore, dl, stats, loss, err,
+                                       ws, nws, _stream_ptr() if stream is None else stream)
+        if rc:
+            _lib.check(rc, "simt_head_fwdbwd")
+
+    def scale(self, grad_out=None, stream=None):
+        B, CK, C, h, w, H, W = self.shape
+        _, _, stats, _, dl, dT, _ = self._p
+        rc = self.lib.simt_head_scale(dl, B * CK * h * w, stats, CK, C,
+                                      None if grad_out is None else grad_out.data_ptr(), dT,
+                                      _stream_ptr() if stream is None else stream)
+        if rc:
+            _lib.check(rc, "simt_head_scale")
+
+    def step(self, logits, T, labels, grad_out=None):
+        stream = _stream_ptr()
+        self.fwdbwd(logits, T, labels, stream)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+        self.scale(grad_out, stream)
+        return self.loss, self.dlogits, self.dT
+
+    def global_loss(self):
+        """loss over the all-reduced stats (sharded runs); a 0-dim f64 tensor, no sync."""
+        return self.stats[0] / self.stats[1]

@@ -33,10 +33,10 @@ def test_head_vs_reference_golden(name, int64_labels):
     _check(dT, g["dT_f64"], "dT vs fp64 reference")
 
 
-@pytest.mark.parametrize("lpr", [1, 2])
-@pytest.mark.parametrize("tile", [(8, 8), (4, 8), (2, 4), (1, 1), (3, 16)])
+@pytest.mark.parametrize("lpr", [2, 4])
+@pytest.mark.parametrize("tile", [(1, 0), (2, 0), (3, 0), (8, 0), (32, 0)])
 def test_head_tilings_and_lane_splits_agree(lpr, tile):
-    """Every tiling / lanes-per-run configuration is the same function."""
+    """Every unit height (cell-rows per warp unit) / lanes-per-cell configuration is the same function."""
     from simt_b200 import _lib
     g = load_golden("head_cfg1_tile")
     lib = _lib.load()
