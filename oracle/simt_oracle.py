@@ -281,9 +281,11 @@ def synth_head_inputs(B, CK, h, w, H, W, *, C=19, seed=1234, coherent=True, igno
     if coherent:
         pdist = np.full(C, 1.0 / C) if class_dist is None else np.asarray(class_dist, dtype=np.float64)
         pdist = pdist / pdist.sum()
-        bh, bw = -(-H // block), -(-W // block)
+        by, bx = (block, block) if np.isscalar(block) else block     # (rows, cols) of a constant block
+        bh, bw = -(-H // by) + 1, -(-W // bx) + 1
         coarse = rng.choice(C, size=(B, bh, bw), p=pdist)
-        lab = np.repeat(np.repeat(coarse, block, axis=1), block, axis=2)[:, :H, :W]
+        oy, ox = (by // 3, bx // 3) if not np.isscalar(block) else (0, 0)   # tuple blocks are also shifted
+        lab = np.repeat(np.repeat(coarse, by, axis=1), bx, axis=2)[:, oy:oy + H, ox:ox + W]
     else:
         lab = rng.integers(0, C, size=(B, H, W))
     lab = lab.astype(np.uint8)

@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimt_b200.so")
+LIB_PATH = os.environ.get("SIMT_B200_LIB") or os.path.join(_HERE, "libsimt_b200.so")  # env override: A/B builds
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/simt_b200.h one to one

@@ -39,6 +39,7 @@
 //   finalize kernel.  Units are claimed dynamically, so the grouping of the fp64 partial sums
 //   (and the order of the fp32 red.adds into dLogits, as in torch's own CUDA backward of
 //   upsample_bilinear2d) is not run-to-run deterministic in the last bit.
+#include <type_traits>
 #include "common.cuh"
 
 namespace simt {
@@ -65,6 +66,7 @@ struct HeadArgs {
   double* part_loss;    // [grid]
   long long* part_cnt;  // [grid]
   int* err;
+  int label_words_ok;  // uint8 labels: buffer 4-byte aligned and a multiple of 4 bytes long
 };
 
 // ---- pixel <-> cell mapping, identical float arithmetic on host and device ----------
@@ -169,43 +171,166 @@ __device__ __forceinline__ void warp_flush_dT(float (&D)[CPL], int old, bool nee
   __syncwarp();
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2: two fp32 lanes per issue slot) ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
+static constexpr float kPadLogit = -1.0e30f;  // padded channels: exp2 -> 0, no inf/NaN arithmetic
+
+// ---- label fetch -----------------------------------------------------------------------------
+// A run's first 8 labels travel as one 64-bit word of raw label bytes (pixels past the run's end
+// are filled with 0xFF, which is never a valid class because C <= 254).  uint8 labels are fetched
+// as three ALIGNED 32-bit words covering the (unaligned) run and are only funnel-shifted together
+// when the row is processed, one row after the loads were issued, so their latency is hidden
+// behind the previous row's arithmetic.  int64 labels (the reference's dtype) are converted at
+// load time (slower, drop-in path).
+struct RawRun {
+  unsigned w0, w1, w2, sh;  // uint8: aligned words + byte shift ; int64: w0/w1 hold the packed bytes
+};
+
+__device__ __forceinline__ unsigned long long fill_tail(unsigned long long v, int n) {
+  const unsigned long long keep = (n >= 8) ? ~0ULL : ((1ULL << (8 * (n < 0 ? 0 : n))) - 1ULL);
+  return v | ~keep;
+}
+
+template <typename LabelT>
+struct LabelFetch;
+
+template <>
+struct LabelFetch<uint8_t> {
+  // words_ok: the label buffer is 4-byte aligned and its size a multiple of 4 (so aligned word
+  // loads never leave the buffer except past `end`, which is guarded)
+  static __device__ __forceinline__ RawRun issue(const uint8_t* labels, long long idx, int n, const uint8_t* end,
+                                                 bool words_ok, int, int) {
+    RawRun r;
+    if (words_ok) {
+      const uint8_t* a = labels + idx;
+      const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+      const unsigned* p = reinterpret_cast<const unsigned*>(ai & ~(uintptr_t)3);
+      r.sh = (unsigned)(ai & 3) * 8u;
+      const unsigned* e = reinterpret_cast<const unsigned*>(end);
+      r.w0 = (n > 0 && p < e) ? __ldg(p) : 0xffffffffu;
+      r.w1 = (n > 0 && p + 1 < e) ? __ldg(p + 1) : 0xffffffffu;
+      r.w2 = (n > 0 && p + 2 < e) ? __ldg(p + 2) : 0xffffffffu;
+    } else {
+      unsigned long long v = ~0ULL;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < n) v = (v & ~(0xffULL << (8 * q))) | ((unsigned long long)__ldg(labels + idx + q) << (8 * q));
+      r.w0 = (unsigned)v; r.w1 = (unsigned)(v >> 32); r.w2 = 0xffffffffu; r.sh = 0u;
+    }
+    return r;
+  }
+  static __device__ __forceinline__ unsigned long long finish(const RawRun& r, int n) {
+    const unsigned lo = __funnelshift_r(r.w0, r.w1, r.sh);
+    const unsigned hi = __funnelshift_r(r.w1, r.w2, r.sh);
+    return fill_tail(((unsigned long long)hi << 32) | lo, n);
+  }
+  static __device__ __forceinline__ unsigned one(const uint8_t* labels, long long idx, int, int) {
+    return (unsigned)__ldg(labels + idx);
+  }
+};
+
+template <>
+struct LabelFetch<long long> {
+  // int64 -> byte code: valid class as is, ignore/negative -> ign8 (or 0xFF), anything else -> 0xFE
+  static __device__ __forceinline__ unsigned one(const long long* labels, long long idx, int ignore, int C) {
+    const long long y = __ldg(labels + idx);
+    if (y == (long long)ignore || y < 0) return (ignore >= 0 && ignore <= 255) ? (unsigned)ignore : 0xffu;
+    return (y < (long long)C) ? (unsigned)y : 0xfeu;
+  }
+  static __device__ __forceinline__ RawRun issue(const long long* labels, long long idx, int n, const long long*,
+                                                 bool, int ignore, int C) {
+    unsigned long long v = ~0ULL;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < n) v = (v & ~(0xffULL << (8 * q))) | ((unsigned long long)one(labels, idx + q, ignore, C) << (8 * q));
+    RawRun r;
+    r.w0 = (unsigned)v; r.w1 = (unsigned)(v >> 32); r.w2 = 0xffffffffu; r.sh = 0u;
+    return r;
+  }
+  static __device__ __forceinline__ unsigned long long finish(const RawRun& r, int n) {
+    return fill_tail(((unsigned long long)r.w1 << 32) | r.w0, n);
+  }
+};
+
+static constexpr int kEdgeRows = 16;  // pixel rows per cell-row whose edge column is staged in smem
+
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
+  static_assert(CPL % 2 == 0, "channels per lane are processed as fp32x2 pairs");
   constexpr bool BWD = (MODE != MODE_FWD);
+  constexpr int NP = CPL / 2;    // channel pairs per lane
   constexpr int CKP = CPL * LPR;
   constexpr int CPW = 32 / LPR;  // cells per warp unit
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CK = A.CK, C = A.C;
-  double* tiles = reinterpret_cast<double*>(smem_raw);                               // [NT/32][C*CKP] (BWD)
-  float* Ts = reinterpret_cast<float*>(smem_raw + (BWD ? (size_t)(NT / 32) * C * CKP * 8 : 0));  // [C][CKP]
-  __shared__ double red_d[NT / 32];
-  __shared__ long long red_i[NT / 32];
+  // [NW][4][NP][32] float2: the cell corners of every lane (log2 domain), re-read once per pixel row
+  float2* Lsm = reinterpret_cast<float2*>(smem_raw);
+  unsigned char* sp = smem_raw + (size_t)NW * 4 * NP * 32 * sizeof(float2);
+  double* tiles = reinterpret_cast<double*>(sp);                      // [NW][C*CKP] dT tiles (BWD)
+  sp += BWD ? (size_t)NW * C * CKP * 8 : 0;
+  float* Ts = reinterpret_cast<float*>(sp);                           // [C][CKP] = -T^T
+  sp += (size_t)C * CKP * 4;
+  float* Esm = reinterpret_cast<float*>(sp);                          // [NW][kEdgeRows][CKP + 1] edge column (BWD)
+  sp += BWD ? (size_t)NW * kEdgeRows * (CKP + 1) * 4 : 0;
+  int* xs_tab = reinterpret_cast<int*>(sp);                           // [ncx + 1] first pixel column of every cell
+  int* ys_tab = xs_tab + (A.ncx + 1);                                 // [ncy + 1] first pixel row of every cell-row
+  __shared__ double red_d[NW];
+  __shared__ long long red_i[NW];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int sub = (LPR > 1) ? (tid & (LPR - 1)) : 0;
-  const unsigned gmask = (LPR == 1) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
   const int kbase = sub * CPL;
   const int pidx = lane / LPR;  // this lane group's cell within the unit
   const LabelT* labels = reinterpret_cast<const LabelT*>(A.labels);
+  const LabelT* labels_end = labels + (long long)A.B * A.H * A.W;
   const int h = A.h, w = A.w;
+  const int ign8 = (A.ignore >= 0 && A.ignore <= 255) ? A.ignore : 256;
+  float2* Lw = Lsm + (size_t)(tid >> 5) * 4 * NP * 32 + lane;  // + (arr * NP + q) * 32
+  float* Ew = Esm + (size_t)(tid >> 5) * kEdgeRows * (CKP + 1);
 
-  // ---- one-time per CTA: T transposed ([y][k], zero padded) and the per-warp dT tiles ----
+  // ---- one-time per CTA: -T transposed ([y][k], zero padded), dT tiles, pixel/cell tables ----
   for (int i = tid; i < C * CKP; i += NT) {
     int y = i / CKP, k = i - y * CKP;
     float v = 0.f;
     if (k < CK) v = A.T ? __ldg(A.T + (size_t)k * C + y) : (k == y ? 1.f : 0.f);
-    Ts[i] = v;
+    Ts[i] = -v;
   }
   if (BWD)
-    for (int i = tid; i < (NT / 32) * C * CKP; i += NT) tiles[i] = 0.0;
+    for (int i = tid; i < NW * C * CKP; i += NT) tiles[i] = 0.0;
+  for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
+  for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
   double* wt = tiles + (size_t)(tid >> 5) * C * CKP;
   __syncthreads();
 
-  float D[CPL];   // dT accumulators for the thread's current label column
-  float Tc[CPL];  // T[:, cur] for this lane's channels
+  float2 D2[NP];     // dT accumulators (p_k / q) for the thread's current label column
+  float2 nTc[NP];    // -T[:, cur] for this lane's channels
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) { D[j] = 0.f; Tc[j] = 0.f; }
+  for (int q = 0; q < NP; ++q) { D2[q] = make_float2(0.f, 0.f); nTc[q] = make_float2(0.f, 0.f); }
   int cur = -1;
   double loss_d = 0.0;  // sum of log2 q over this thread's valid pixels
   long long cnt = 0;
@@ -215,6 +340,21 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     unsigned long long u = 0;
     if (lane == 0) u = atomicAdd(A.counter, 1ULL);
     return (long long)__shfl_sync(0xffffffffu, u, 0);
+  };
+  auto switch_column = [&](int y) {
+    cur = y;
+    const float2* src = reinterpret_cast<const float2*>(Ts + y * CKP + kbase);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) nTc[q] = src[q];
+  };
+  auto flush_lane = [&]() {  // per-lane flush (label change inside a run; rare on coherent maps)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const float v = (j & 1) ? D2[j >> 1].y : D2[j >> 1].x;
+      if (kbase + j < CK) atomicAdd(&wt[cur * CKP + kbase + j], (double)v);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) D2[q] = make_float2(0.f, 0.f);
   };
 
   long long unit = claim();
@@ -226,198 +366,332 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     const int uy = urem / A.units_x, ux = urem - uy * A.units_x;
     const int cx = ux * CPW + pidx;
     const bool cell_ok = cx < A.ncx;
-    const int xa = cell_ok ? first_px_of_cell(cx, A.sx, A.ncx, A.W) : 0;
-    const int xb = cell_ok ? first_px_of_cell(cx + 1, A.sx, A.ncx, A.W) : 0;
-    const bool last_cell = cell_ok && (pidx == CPW - 1 || cx == A.ncx - 1);
-    const int nrun = xb - xa;
+    const int xa = cell_ok ? xs_tab[cx] : 0;
+    const int nrun = cell_ok ? xs_tab[cx + 1] - xa : 0;
+    const int ncell_u = min(CPW, A.ncx - ux * CPW);            // cells of this unit (warp-uniform)
+    const bool last_cell = pidx == ncell_u - 1;
     const int nmax = __reduce_max_sync(0xffffffffu, nrun);
     const int gx0 = min(cx, w - 1), gx1 = min(cx + 1, w - 1);
+    const int edge_gx = min(ux * CPW + ncell_u, w - 1);          // node column right of the unit
     float loss_acc = 0.f;
 
-    const int cy_end = min(A.ncy, (uy + 1) * A.ur);
-    for (int cy = uy * A.ur; cy < cy_end; ++cy) {
-      const int Y0 = first_px_of_cell(cy, A.sy, A.ncy, A.H);
-      const int Y1 = first_px_of_cell(cy + 1, A.sy, A.ncy, A.H);
+    const int cy_begin = uy * A.ur, cy_end = min(A.ncy, (uy + 1) * A.ur);
+    const int Yfirst = ys_tab[cy_begin];
+    const int Ylast = ys_tab[cy_end];  // one past the unit's last pixel row
+    RawRun raw_next = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u};
+    if (Yfirst < Ylast)
+      raw_next = LabelFetch<LabelT>::issue(labels, ((long long)b * A.H + Yfirst) * A.W + xa, nrun, labels_end,
+                                           A.label_words_ok != 0, A.ignore, C);
+
+    for (int cy = cy_begin; cy < cy_end; ++cy) {
+      const int Y0 = ys_tab[cy];
+      const int Y1 = ys_tab[cy + 1];
       if (Y1 <= Y0) continue;  // warp-uniform
       const int gy0 = min(cy, h - 1), gy1 = min(cy + 1, h - 1);
-      // ---- the cell's 4 corners for this lane's channels, in registers (log2 domain) ----
-      float l0[CPL], dl0[CPL], l1[CPL], dl1[CPL];
+      const bool edge_smem = BWD && (Y1 - Y0 <= kEdgeRows);
+      // ---- stage the cell's 4 corners of this lane's channels (log2 domain) in the warp's smem slice ----
       {
         const float* src = A.logits + ((size_t)b * CK + kbase) * h * w;
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-          if (cell_ok && kbase + j < CK) {
-            const float* p = src + (size_t)j * h * w;
-            c00 = __ldg(p + gy0 * w + gx0); c01 = __ldg(p + gy0 * w + gx1);
-            c10 = __ldg(p + gy1 * w + gx0); c11 = __ldg(p + gy1 * w + gx1);
+        for (int q = 0; q < NP; ++q) {
+          float c00[2], c01[2], c10[2], c11[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = 2 * q + t;
+            c00[t] = c01[t] = kPadLogit; c10[t] = c11[t] = kPadLogit;
+            if (!cell_ok) { c00[t] = c01[t] = c10[t] = c11[t] = 0.f; }
+            else if (kbase + j < CK) {
+              const float* p = src + (size_t)j * h * w;
+              c00[t] = __ldg(p + gy0 * w + gx0) * kLog2e; c01[t] = __ldg(p + gy0 * w + gx1) * kLog2e;
+              c10[t] = __ldg(p + gy1 * w + gx0) * kLog2e; c11[t] = __ldg(p + gy1 * w + gx1) * kLog2e;
+            }
           }
-          l0[j] = c00 * kLog2e; dl0[j] = (c10 - c00) * kLog2e;
-          l1[j] = c01 * kLog2e; dl1[j] = (c11 - c01) * kLog2e;
+          Lw[(0 * NP + q) * 32] = make_float2(c00[0], c00[1]);
+          Lw[(1 * NP + q) * 32] = make_float2(c10[0] - c00[0], c10[1] - c00[1]);
+          Lw[(2 * NP + q) * 32] = make_float2(c01[0], c01[1]);
+          Lw[(3 * NP + q) * 32] = make_float2(c11[0] - c01[0], c11[1] - c01[1]);
         }
+        __syncwarp();
       }
-      float Vt[CPL], Vb[CPL];
+      float2 Vt[NP], Vb[NP];
       if (BWD) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) { Vt[j] = 0.f; Vb[j] = 0.f; }
+        for (int q = 0; q < NP; ++q) { Vt[q] = make_float2(0.f, 0.f); Vb[q] = make_float2(0.f, 0.f); }
       }
 
       for (int Y = Y0; Y < Y1; ++Y) {
         const float ly = lambda_of(Y, A.sy, cy);
-        const long long rowbase = ((long long)b * A.H + Y) * A.W;
-        if (Y + 1 < Y1 && xb > xa)  // next row's labels on their way
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + rowbase + A.W + xa));
-        if (BWD) {
-          // Row boundary, warp converged: if the run's first valid label differs from the column
-          // the D[] accumulators belong to, flush them collectively before switching column.
-          int first_lab = -1;
-          for (int X = xa; X < xb; ++X) {
-            const int y = load_label<LabelT>(labels, rowbase + X);
-            if (y != A.ignore && y >= 0 && y < C) { first_lab = y; break; }
-          }
-          const bool sw = first_lab >= 0 && first_lab != cur;
-          const bool need = sw && cur >= 0;
-          if (__any_sync(0xffffffffu, need)) warp_flush_dT<CPL, LPR>(D, cur, need, wt, CKP, CK, kbase, lane);
-          if (sw) {
-            cur = first_lab;
+        const long long rowbase = ((long long)b * A.H + Y) * A.W + xa;
+        const unsigned long long codes = LabelFetch<LabelT>::finish(raw_next, nrun);
+        if (Y + 1 < Ylast)  // next row's labels are in flight during this row's arithmetic
+          raw_next = LabelFetch<LabelT>::issue(labels, rowbase + A.W, nrun, labels_end, A.label_words_ok != 0,
+                                               A.ignore, C);
+        // ---- classify the row's (up to 8) labels: first valid label, label-uniform?, contract check ----
+        int first_lab = -1;
+        bool row_uni = true;
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) Tc[j] = Ts[cur * CKP + kbase + j];
+        for (int q = 0; q < 8; ++q) {
+          const int c = (int)((codes >> (8 * q)) & 0xffu);
+          const bool valid = c < C && c != ign8;
+          if (valid) {
+            if (first_lab < 0) first_lab = c;
+            row_uni = row_uni && (c == first_lab);
+          } else if (c != ign8 && q < nrun) {
+            bad_label = true;  // neither a class nor the ignore label
           }
-        }
-        float Gs[CPL], G1[CPL];
-        if (BWD) {
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) { Gs[j] = 0.f; G1[j] = 0.f; }
         }
         {
-          // vertical lerp once per row; a = v0 - M, d = v1 - v0
-          float a[CPL], d[CPL];
-          float M = -INFINITY;
+          // Row boundary, warp converged: if the row's label differs from the column the D[] accumulators
+          // belong to, flush them collectively before switching column.
+          const bool sw = first_lab >= 0 && first_lab != cur;
+          if (BWD) {
+            const bool need = sw && cur >= 0;
+            if (__any_sync(0xffffffffu, need))
+              warp_flush_dT<CPL, LPR>(reinterpret_cast<float(&)[CPL]>(D2), cur, need, wt, CKP, CK, kbase, lane);
+          }
+          if (sw) switch_column(first_lab);
+        }
+        float2 Gs[NP], G1[NP];
+        if (BWD) {
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            const float v0 = fmaf(ly, dl0[j], l0[j]);
-            const float v1 = fmaf(ly, dl1[j], l1[j]);
-            a[j] = v0;
-            d[j] = v1 - v0;
-            if (kbase + j < CK) M = fmaxf(M, fmaxf(v0, v1));
+          for (int q = 0; q < NP; ++q) { Gs[q] = make_float2(0.f, 0.f); G1[q] = make_float2(0.f, 0.f); }
+        }
+        {
+          // vertical lerp once per row; a = v0 - M, d = v1 - v0  (M = upper bound of the row's logits)
+          float2 a[NP], d[NP];
+          float M = -INFINITY, mlo = -INFINITY;  // max_k max(v0,v1) >= every pixel's max >= max_k min(v0,v1)
+          const float2 ly2 = bcast2(ly);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const float2 v0 = ffma2(ly2, Lw[(1 * NP + q) * 32], Lw[(0 * NP + q) * 32]);
+            const float2 v1 = ffma2(ly2, Lw[(3 * NP + q) * 32], Lw[(2 * NP + q) * 32]);
+            a[q] = v0;
+            d[q] = ffma2(v0, bcast2(-1.f), v1);
+            M = fmaxf(M, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
+            mlo = fmaxf(mlo, fmaxf(fminf(v0.x, v1.x), fminf(v0.y, v1.y)));
           }
           M = group_max<LPR>(M, 0xffffffffu);
+          mlo = group_max<LPR>(mlo, 0xffffffffu);
+          // exp-sum >= 2^(mlo - M): no pixel of this row can underflow the softmax denominator
+          const bool range_safe = (M - mlo) < 38.f;
+          const float2 nM = bcast2(-M);
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) a[j] = (kbase + j < CK) ? a[j] - M : -INFINITY;
+          for (int q = 0; q < NP; ++q) a[q] = fadd2(a[q], nM);
 
-          // The pixel loop is WARP-UNIFORM (nmax iterations, invalid lanes predicated off): the lane
-          // groups exchange partial sums with full-mask shuffles, which must not sit behind a
-          // divergent `continue` (group-masked shuffles serialise the 32/LPR groups).
-          for (int i = 0; i < nmax; ++i) {
-            const int X = xa + i;
-            const bool inb = i < nrun;
-            const int y = inb ? load_label<LabelT>(labels, rowbase + X) : A.ignore;
-            bool valid = inb && y != A.ignore && y >= 0;
-            if (valid && y >= C) { bad_label = true; valid = false; }
-            if (valid && y != cur) {
-              // label changed INSIDE a run (rare on coherent maps): per-lane flush
-              if (BWD && cur >= 0) {
+          // One step = two pixels of every lane's run (two independent MUFU/FMA chains per lane,
+          // channel pairs packed into fp32x2 instructions).  WARP-UNIFORM: lane groups exchange partial
+          // sums with full-mask shuffles, so invalid lanes/pixels are predicated off (w0/w1), never
+          // branched around.
+          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1) {
+            const float2 L0 = bcast2(lam0), L1 = bcast2(lam1);
+            float2 e0[NP], e1[NP];
+            float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0, ns0 = sum0, ns1 = sum0;
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                  if (kbase + j < CK) atomicAdd(&wt[cur * CKP + kbase + j], (double)D[j]);
-                  D[j] = 0.f;
-                }
-              }
-              cur = y;
-#pragma unroll
-              for (int j = 0; j < CPL; ++j) Tc[j] = Ts[y * CKP + kbase + j];
+            for (int q = 0; q < NP; ++q) {
+              const float2 t0 = ffma2(L0, d[q], a[q]);
+              const float2 t1 = ffma2(L1, d[q], a[q]);
+              e0[q] = make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+              e1[q] = make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+              sum0 = fadd2(sum0, e0[q]);
+              sum1 = fadd2(sum1, e1[q]);
+              ns0 = ffma2(e0[q], nTc[q], ns0);
+              ns1 = ffma2(e1[q], nTc[q], ns1);
             }
-            const float lam = lambda_of(X, A.sx, cx);
-            float e[CPL];
-            float sum0 = 0.f, sum1 = 0.f, s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-              e[j] = ex2_approx(fmaf(lam, d[j], a[j]));
-              if (j & 1) { sum1 += e[j]; s1 = fmaf(e[j], Tc[j], s1); }
-              else       { sum0 += e[j]; s0 = fmaf(e[j], Tc[j], s0); }
-            }
-            float sum = group_sum<LPR>(sum0 + sum1, 0xffffffffu);
-            float s = s0 + s1;
-            if (__any_sync(0xffffffffu, valid && sum < 1e-12f)) {
+            float su0 = group_sum<LPR>(sum0.x + sum0.y, 0xffffffffu);
+            float su1 = group_sum<LPR>(sum1.x + sum1.y, 0xffffffffu);
+            float s0 = -(ns0.x + ns0.y), s1 = -(ns1.x + ns1.y);
+            if (decltype(check_underflow)::value &&
+                __any_sync(0xffffffffu, (w0 && su0 < 1e-12f) || (w1 && su1 < 1e-12f))) {
               // the row-level bound M was far above some pixel's true max: redo with the exact max
-              float tm = -INFINITY;
+              float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < CPL; ++j) tm = fmaxf(tm, fmaf(lam, d[j], a[j]));
-              tm = group_max<LPR>(tm, 0xffffffffu);
-              sum = 0.f; s = 0.f;
-#pragma unroll
-              for (int j = 0; j < CPL; ++j) {
-                e[j] = ex2_approx(fmaf(lam, d[j], a[j]) - tm);
-                sum += e[j];
-                s = fmaf(e[j], Tc[j], s);
+              for (int q = 0; q < NP; ++q) {
+                const float2 t0 = ffma2(L0, d[q], a[q]), t1 = ffma2(L1, d[q], a[q]);
+                tm0 = fmaxf(tm0, fmaxf(t0.x, t0.y));
+                tm1 = fmaxf(tm1, fmaxf(t1.x, t1.y));
               }
-              sum = group_sum<LPR>(sum, 0xffffffffu);
+              tm0 = group_max<LPR>(tm0, 0xffffffffu);
+              tm1 = group_max<LPR>(tm1, 0xffffffffu);
+              su0 = su1 = s0 = s1 = 0.f;
+#pragma unroll 1
+              for (int q = 0; q < NP; ++q) {
+                const float2 t0 = ffma2(L0, d[q], a[q]), t1 = ffma2(L1, d[q], a[q]);
+                e0[q] = make_float2(ex2_approx(t0.x - tm0), ex2_approx(t0.y - tm0));
+                e1[q] = make_float2(ex2_approx(t1.x - tm1), ex2_approx(t1.y - tm1));
+                su0 += e0[q].x + e0[q].y;
+                su1 += e1[q].x + e1[q].y;
+                s0 -= e0[q].x * nTc[q].x + e0[q].y * nTc[q].y;
+                s1 -= e1[q].x * nTc[q].x + e1[q].y * nTc[q].y;
+              }
+              su0 = group_sum<LPR>(su0, 0xffffffffu);
+              su1 = group_sum<LPR>(su1, 0xffffffffu);
             }
-            s = group_sum<LPR>(s, 0xffffffffu);
-            const float rsum = valid ? rcp_approx(sum) : 0.f;
-            if (MODE != MODE_BWD && sub == 0 && valid) loss_acc += lg2_approx(s * rsum);
-            cnt += (sub == 0 && valid);
+            s0 = group_sum<LPR>(s0, 0xffffffffu);
+            s1 = group_sum<LPR>(s1, 0xffffffffu);
+            // 1/sum and 1/s from ONE reciprocal of the product (MUFU is the binding pipe)
+            const float r0 = w0 ? rcp_approx(su0 * s0) : 0.f;
+            const float r1 = w1 ? rcp_approx(su1 * s1) : 0.f;
+            const float rs0 = r0 * s0, rs1 = r1 * s1;    // 1 / sum
+            if (MODE != MODE_BWD) {
+              // log2 q0 + log2 q1 = log2(q0 q1); q in (0, 1] and an invalid pixel contributes q = 1
+              const float q0 = w0 ? s0 * rs0 : 1.f, q1 = w1 ? s1 * rs1 : 1.f;
+              const float qq = q0 * q1;
+              if (qq > 1e-30f) loss_acc += lg2_approx(qq);
+              else loss_acc += lg2_approx(q0) + lg2_approx(q1);
+            }
+            cnt += (int)w0 + (int)w1;
             if (BWD) {
-              const float is = valid ? rcp_approx(s) : 0.f;
-              const float lis = lam * is, lrs = lam * rsum;
+              const float is0 = r0 * su0, is1 = r1 * su1;  // 1 / s
+              const float2 I0 = bcast2(is0), I1 = bcast2(is1);
+              const float2 R0 = bcast2(rs0), R1 = bcast2(rs1);
+              const float2 LI0 = bcast2(lam0 * is0), LI1 = bcast2(lam1 * is1);
+              const float2 LR0 = bcast2(lam0 * rs0), LR1 = bcast2(lam1 * rs1);
 #pragma unroll
-              for (int j = 0; j < CPL; ++j) {
-                const float c = fmaf(-Tc[j], is, rsum);     // (p_k - p_k T_ky / q) / e_k
-                const float c1 = fmaf(-Tc[j], lis, lrs);    // lambda * c
-                Gs[j] = fmaf(e[j], c, Gs[j]);
-                G1[j] = fmaf(e[j], c1, G1[j]);
-                D[j] = fmaf(e[j], is, D[j]);                // p_k / q
+              for (int q = 0; q < NP; ++q) {
+                // c = (p_k - p_k T_ky / q) / e_k = rs - T_ky * is ;  c1 = lambda * c
+                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(nTc[q], I1, R1);
+                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(nTc[q], LI1, LR1);
+                Gs[q] = ffma2(e0[q], ca, Gs[q]);
+                Gs[q] = ffma2(e1[q], cb, Gs[q]);
+                G1[q] = ffma2(e0[q], c1a, G1[q]);
+                G1[q] = ffma2(e1[q], c1b, G1[q]);
+                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q
+                D2[q] = ffma2(e1[q], I1, D2[q]);
+              }
+            }
+          };
+
+          const bool fast_row = row_uni && range_safe;
+          if (nmax <= 8 && __all_sync(0xffffffffu, fast_row)) {
+            // ---- fast row: every lane's valid pixels carry the lane's current label and no pixel can
+            // underflow -> straight-line steps with no votes or branches; unrolled so that the next
+            // step's FFMA2/MUFU issue under the previous step's reduction tail
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+              if (2 * st < nmax) {
+                const unsigned c0 = (unsigned)(codes >> (16 * st)) & 0xffu;
+                const unsigned c1 = (unsigned)(codes >> (16 * st + 8)) & 0xffu;
+                const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
+                const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
+                body(std::false_type{}, lambda_of(xa + 2 * st, A.sx, cx), lambda_of(xa + 2 * st + 1, A.sx, cx), v0, v1);
+              }
+            }
+          } else {
+            // ---- generic row: label changes inside a run, long runs, or extreme logit range ----
+#pragma unroll 1
+            for (int i = 0; i < nmax; i += 2) {
+              unsigned c0, c1;
+              if (i < 8) {  // i is even, so i + 1 < 8 as well
+                c0 = (unsigned)(codes >> (8 * i)) & 0xffu;
+                c1 = (unsigned)(codes >> (8 * i + 8)) & 0xffu;
+              } else {
+                c0 = (i < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + i, A.ignore, C) : 0xffu;
+                c1 = (i + 1 < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + i + 1, A.ignore, C) : 0xffu;
+                if ((c0 >= (unsigned)C && (int)c0 != ign8 && i < nrun) ||
+                    (c1 >= (unsigned)C && (int)c1 != ign8 && i + 1 < nrun))
+                  bad_label = true;
+              }
+              const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
+              const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
+              const bool same = (!v0 || (int)c0 == cur) && (!v1 || (int)c1 == cur);
+              const float lam0 = lambda_of(xa + i, A.sx, cx);
+              const float lam1 = lambda_of(xa + i + 1, A.sx, cx);
+              if (__all_sync(0xffffffffu, same)) {
+                body(std::true_type{}, lam0, lam1, v0, v1);
+              } else {
+                // some lane crosses a label boundary inside its run: one pixel at a time, with a
+                // per-lane column switch in between (still warp-uniform control flow)
+#pragma unroll 1
+                for (int rep = 0; rep < 2; ++rep) {
+                  const unsigned cc = rep ? c1 : c0;
+                  const bool wv = rep ? v1 : v0;
+                  if (wv && (int)cc != cur) {
+                    if (BWD && cur >= 0) flush_lane();
+                    switch_column((int)cc);
+                  }
+                  body(std::true_type{}, rep ? lam1 : lam0, 0.f, wv, false);
+                }
               }
             }
           }
         }
         if (BWD) {
           // node column cx of this row = G0(cx) + G1(cx-1); the left neighbour is LPR lanes below
-          __syncwarp();
-          const float wy1 = ly, wy0 = 1.f - ly;
+          const float2 wy1 = bcast2(ly), wy0 = bcast2(1.f - ly);
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            float prev = __shfl_up_sync(0xffffffffu, G1[j], LPR);
-            if (pidx == 0) prev = 0.f;
-            const float n = (Gs[j] - G1[j]) + prev;
-            Vt[j] = fmaf(wy0, n, Vt[j]);
-            Vb[j] = fmaf(wy1, n, Vb[j]);
+          for (int q = 0; q < NP; ++q) {
+            float px = __shfl_up_sync(0xffffffffu, G1[q].x, LPR);
+            float py = __shfl_up_sync(0xffffffffu, G1[q].y, LPR);
+            if (pidx == 0) { px = 0.f; py = 0.f; }
+            const float2 n = make_float2((Gs[q].x - G1[q].x) + px, (Gs[q].y - G1[q].y) + py);
+            Vt[q] = ffma2(wy0, n, Vt[q]);
+            Vb[q] = ffma2(wy1, n, Vb[q]);
           }
-          if (last_cell) {
-            // right edge of the unit: node column cx+1 belongs to the next unit (or is the image's
-            // last column); add this row's share directly
+          // right edge of the unit: node column edge_gx belongs to the next unit (or is the image's
+          // last column).  Its per-row values wait in the warp's smem slice until the cell-row is done.
+          if (edge_smem) {
+            if (last_cell) {
+              float* er = Ew + (Y - Y0) * (CKP + 1) + kbase;
+#pragma unroll
+              for (int q = 0; q < NP; ++q) { er[2 * q] = G1[q].x; er[2 * q + 1] = G1[q].y; }
+              if (sub == 0) Ew[(Y - Y0) * (CKP + 1) + CKP] = ly;
+            }
+          } else if (last_cell) {
             float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
             const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+            const float w0y = (1.f - ly) * gs, w1y = ly * gs;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
               if (kbase + j < CK) {
                 float* pk = dst + (size_t)j * h * w;
-                atomicAdd(pk + gy0 * w + gx1, wy0 * G1[j] * gs);
-                atomicAdd(pk + gy1 * w + gx1, wy1 * G1[j] * gs);
+                const float g1 = (j & 1) ? G1[j >> 1].y : G1[j >> 1].x;
+                atomicAdd(pk + gy0 * w + edge_gx, w0y * g1);
+                atomicAdd(pk + gy1 * w + edge_gx, w1y * g1);
               }
             }
           }
         }
       }  // rows of the cell-row
 
-      if (BWD && cell_ok) {
-        float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
+      if (BWD) {
+        float* dst = A.dlogits + (size_t)b * CK * h * w;
         const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+        if (cell_ok) {
+          float* dk = dst + (size_t)kbase * h * w;
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          if (kbase + j < CK) {
-            float* pk = dst + (size_t)j * h * w;
-            atomicAdd(pk + gy0 * w + gx0, Vt[j] * gs);
-            atomicAdd(pk + gy1 * w + gx0, Vb[j] * gs);
+          for (int j = 0; j < CPL; ++j) {
+            if (kbase + j < CK) {
+              float* pk = dk + (size_t)j * h * w;
+              const float vt = (j & 1) ? Vt[j >> 1].y : Vt[j >> 1].x;
+              const float vb = (j & 1) ? Vb[j >> 1].y : Vb[j >> 1].x;
+              atomicAdd(pk + gy0 * w + gx0, vt * gs);
+              atomicAdd(pk + gy1 * w + gx0, vb * gs);
+            }
           }
+        }
+        if (edge_smem) {
+          // vertical transposed lerp of the staged edge column: one lane per channel
+          __syncwarp();
+          for (int k = lane; k < CK; k += 32) {
+            float et = 0.f, eb = 0.f;
+            for (int r = 0; r < Y1 - Y0; ++r) {
+              const float g1 = Ew[r * (CKP + 1) + k], lyr = Ew[r * (CKP + 1) + CKP];
+              et = fmaf(1.f - lyr, g1, et);
+              eb = fmaf(lyr, g1, eb);
+            }
+            float* pk = dst + (size_t)k * h * w;
+            atomicAdd(pk + gy0 * w + edge_gx, et * gs);
+            atomicAdd(pk + gy1 * w + edge_gx, eb * gs);
+          }
+          __syncwarp();
         }
       }
     }  // cell-rows of the unit
 
     // per-unit hand-off: fp32 partials of a unit are summed in a fixed order; across units in fp64
-    if (BWD) {
-      warp_flush_dT<CPL, LPR>(D, cur, cur >= 0, wt, CKP, CK, kbase, lane);
-    }
+    if (BWD)
+      warp_flush_dT<CPL, LPR>(reinterpret_cast<float(&)[CPL]>(D2), cur, cur >= 0, wt, CKP, CK, kbase, lane);
     loss_d += (double)loss_acc;
     unit = next_unit;
   }
@@ -429,11 +703,12 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if (lane == 0) { red_d[tid >> 5] = loss_d; red_i[tid >> 5] = cnt; }
+  // every lane of a lane group accumulated the same loss / count: undo the LPR-fold replication
+  if (lane == 0) { red_d[tid >> 5] = loss_d / (double)LPR; red_i[tid >> 5] = cnt / LPR; }
   __syncthreads();
   if (tid == 0) {
     double tl = 0; long long tc = 0;
-    for (int wv = 0; wv < NT / 32; ++wv) { tl += red_d[wv]; tc += red_i[wv]; }
+    for (int wv = 0; wv < NW; ++wv) { tl += red_d[wv]; tc += red_i[wv]; }
     A.part_loss[blockIdx.x] = tl;
     A.part_cnt[blockIdx.x] = tc;
   }
@@ -442,7 +717,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     for (int i = tid; i < C * CKP; i += NT) {
       double v = 0.0;
 #pragma unroll
-      for (int wv = 0; wv < NT / 32; ++wv) v += tiles[(size_t)wv * C * CKP + i];
+      for (int wv = 0; wv < NW; ++wv) v += tiles[(size_t)wv * C * CKP + i];
       pd[i] = v;
     }
   }
@@ -554,16 +829,23 @@ static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* gr
 }
 
 // channel-count -> (CPL, LPR, threads, min CTAs/SM) instantiations
+#ifndef SIMT_MINB_BWD
+#define SIMT_MINB_BWD 3
+#endif
+#ifndef SIMT_MINB_FWD
+#define SIMT_MINB_FWD 4
+#endif
 #define SIMT_HEAD_CONFIGS(X) \
-  X(10, 2, 128, 3)           \
-  X(6, 4, 128, 4)            \
-  X(9, 4, 128, 3)            \
-  X(16, 4, 128, 2)
+  X(10, 2, 128, SIMT_MINB_FWD, SIMT_MINB_BWD)        \
+  X(6, 4, 128, 4, 4)         \
+  X(10, 4, 128, 4, 3)        \
+  X(16, 4, 128, 3, 2)
 
 template <int MODE, typename LabelT>
 static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
-#define X(cpl, lpr, nt, minb) \
-  if (P.CPL == cpl && P.LPR == lpr) return launch_cfg<cpl, lpr, MODE, LabelT, nt, minb>(A, P, st, grid_out);
+#define X(cpl, lpr, nt, minb_fwd, minb_bwd) \
+  if (P.CPL == cpl && P.LPR == lpr)          \
+    return launch_cfg<cpl, lpr, MODE, LabelT, nt, (MODE == MODE_FWD ? minb_fwd : minb_bwd)>(A, P, st, grid_out);
   SIMT_HEAD_CONFIGS(X)
 #undef X
   return SIMT_EUNSUPPORTED;
@@ -583,7 +865,7 @@ static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan
 static int choose_config(int CK, int lpr_req, Plan* P) {
   struct Cfg { int cpl, lpr, nt, minb; };
   static const Cfg cfgs[] = {
-#define X(cpl, lpr, nt, minb) {cpl, lpr, nt, minb},
+#define X(cpl, lpr, nt, minb_fwd, minb_bwd) {cpl, lpr, nt, minb_fwd},
       SIMT_HEAD_CONFIGS(X)
 #undef X
   };
@@ -622,7 +904,9 @@ static int make_plan(int mode, int B, int CK, int C, int h, int w, int H, int W,
   A->units_x = (A->ncx + cpw - 1) / cpw;
   A->nunits = (long long)B * A->units_y * A->units_x;
   const bool bwd = mode != MODE_FWD;
-  P->smem = (bwd ? (size_t)(P->NT / 32) * C * P->CKP * 8 : 0) + (size_t)C * P->CKP * 4;
+  const size_t nw = (size_t)(P->NT / 32);
+  P->smem = nw * 4 * (P->CPL / 2) * 32 * 8 + (bwd ? nw * C * P->CKP * 8 : 0) + (size_t)C * P->CKP * 4 +
+            (bwd ? nw * kEdgeRows * (P->CKP + 1) * 4 : 0) + (size_t)(A->ncx + A->ncy + 2) * 4;
   return 0;
 }
 
@@ -650,6 +934,8 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   A.logits = logits; A.T = T; A.labels = labels;
   A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = ignore;
   A.gscale = gscale; A.dlogits = dlogits; A.err = err_flag;
+  A.label_words_ok = (label_bytes == 1 && (reinterpret_cast<uintptr_t>(labels) & 3) == 0 &&
+                      (((long long)B * H * W) & 3) == 0) ? 1 : 0;
   rc = make_plan(mode, B, CK, C, h, w, H, W, &A, &P);
   if (rc) return rc;
   DeviceInfo di;
