@@ -157,7 +157,32 @@ int simt_class_hist(const void* a, int a_bytes, long long n, int n_bins,
                     long long* hist, void* stream);
 int simt_label_map(const uint8_t* in, long long n, const uint8_t* lut256, long long* out, void* stream);
 
-/* benchmark hook: 0 = automatic, 1 = lane-private byte counters, 2 = shared atomics */
+/* ------------------------------------------------------------------------- *
+ * T regularisers (tools/trainV2_simt.py:412-421) and anchor statistics (:375-384).
+ *
+ * simt_t_regularizers: ONE single-CTA launch for one head.
+ *   T [CK, C], W [CK, CK] f32 (W may be NULL: volume only)
+ *   out2[0] = -||W T||_F^2          (:414-415, this head's term of NTM_Convex_loss)
+ *   out2[1] = 0.5 log|det(T^T T)|   (:417-418; 0 when not finite, the guard of :420-421)
+ *   dT_convex = -2 W^T W T, dW_convex = -2 W T T^T, dT_volume = T (T^T T)^-1 (zeros when not finite)
+ *
+ * simt_anchor_stats: Anchor_index / Exist_label of :375-377 from the LOW-res logits [B, CK, h, w]:
+ *   anchor_idx[k] = arg-max over the B*H*W upsampled pixels (NHWC-flatten order) of channel k,
+ *   anchor_val[k] (optional) the maximum, exist_mask bit k = class k is the arg-max at some pixel
+ *   (CK <= 64).  scratch: CK u64 words.  Smallest pixel / class wins ties.
+ *
+ * simt_bilinear_gather: rows[r][c] = upsample(src)[b, c, Y, X] at flat pixel pixel_idx[r]
+ *   (labelC_flat[Anchor_index], :378) without materialising the upsampled tensor.
+ * ------------------------------------------------------------------------- */
+int simt_t_regularizers(const float* T, const float* W, int CK, int C, float* out2,
+                        float* dT_convex, float* dT_volume, float* dW_convex, void* stream);
+int simt_anchor_stats(const float* logits, int B, int CK, int h, int w, int H, int W,
+                      long long* anchor_idx, float* anchor_val, unsigned long long* exist_mask,
+                      unsigned long long* scratch, void* stream);
+int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, int W,
+                         const long long* pixel_idx, int n, float* rows, void* stream);
+
+/* benchmark hook (process-global): `mode` is reserved; warps per CTA and 128-bit loads in flight per lane; 0 = automatic */
 void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
 
 #ifdef __cplusplus

@@ -294,15 +294,24 @@ def synth_head_inputs(B, CK, h, w, H, W, *, C=19, seed=1234, coherent=True, igno
     return logits, torch.from_numpy(np.ascontiguousarray(lab))
 
 
-def synth_eval_pair(H, W, *, seed=1234, coherent=True, block=32, n_raw=34, n_pred=19):
-    """(raw-id gt uint8 [H,W] in 0..n_raw-1, pred uint8 [H,W] in 0..n_pred-1)."""
+def synth_eval_pair(H, W, *, seed=1234, coherent=True, block=32, n_raw=34, n_pred=19, noise=0.05):
+    """(raw-id gt uint8 [H,W] in 0..n_raw-1, pred uint8 [H,W] in 0..n_pred-1).  Coherent maps are constant
+    over blocks (gt and pred on DIFFERENT, mutually shifted block grids so their boundaries do not line
+    up); ``noise`` = fraction of pred pixels replaced by a random class."""
     rng = np.random.default_rng(seed)
     if coherent:
-        bh, bw = -(-H // block), -(-W // block)
-        gt = np.repeat(np.repeat(rng.integers(0, n_raw, size=(bh, bw)), block, 0), block, 1)[:H, :W]
-        pr = np.repeat(np.repeat(rng.integers(0, n_pred, size=(bh, bw)), block, 0), block, 1)[:H, :W]
-        flip = rng.random((H, W)) < 0.05
-        pr = np.where(flip, rng.integers(0, n_pred, size=(H, W)), pr)
+        by, bx = (block, block) if np.isscalar(block) else block
+
+        def blocks(n, by_, bx_, oy, ox):
+            bh, bw = -(-H // by_) + 2, -(-W // bx_) + 2
+            m = rng.integers(0, n, size=(bh, bw))
+            return np.repeat(np.repeat(m, by_, 0), bx_, 1)[oy:oy + H, ox:ox + W]
+
+        gt = blocks(n_raw, by, bx, 0, 0)
+        pr = blocks(n_pred, max(1, (by * 3) // 4), max(1, (bx * 5) // 4), by // 3, bx // 5)
+        if noise > 0:
+            flip = rng.random((H, W)) < noise
+            pr = np.where(flip, rng.integers(0, n_pred, size=(H, W)), pr)
     else:
         gt = rng.integers(0, n_raw, size=(H, W))
         pr = rng.integers(0, n_pred, size=(H, W))

@@ -90,19 +90,20 @@ def main():
     # ---- histograms: BIG launches (32 images = 64 Mi pixels per launch), 3 rotating sets > L2 ----------
     lut = torch.from_numpy(simt_b200.build_lut(O.CITYSCAPES_LABEL2TRAIN)).to(dev)
     nimg, nsets = 32, 3
-    for coherent in (True, False):
+    for coherent in ('clean', 'noisy', False):
         gt_sets, pr_sets = [], []
         for s_ in range(nsets):
             gts, prs = [], []
             for i in range(8):
-                gt, pr = O.synth_eval_pair(1024, 2048, seed=8 * s_ + i, coherent=coherent)
+                gt, pr = O.synth_eval_pair(1024, 2048, seed=8 * s_ + i, coherent=bool(coherent), block=(96, 160) if coherent else 32,
+                                            noise=0.05 if coherent == 'noisy' else 0.0)
                 gts.append(torch.from_numpy(gt)); prs.append(torch.from_numpy(pr))
             gt_sets.append(torch.stack(gts).repeat(nimg // 8, 1, 1).to(dev).reshape(-1))
             pr_sets.append(torch.stack(prs).repeat(nimg // 8, 1, 1).to(dev).reshape(-1))
         npx = gt_sets[0].numel()
         for (rows, cols, use_lut) in ((19, 19, True), (34, 19, False), (19, 1, False)):
-            for mode in (1, 2):
-                for warps, unroll in ((8, 4), (8, 2), (16, 2), (16, 4), (4, 4), (16, 1)):
+            for mode in (0,):
+                for warps, unroll in ((16, 2), (16, 4), (16, 1), (8, 4), (8, 2), (32, 2)):
                     lib.simt_hist_set_tuning(mode, warps, unroll)
                     hist = torch.zeros(rows * cols, dtype=torch.int64, device=dev)
                     try:
@@ -123,7 +124,7 @@ def main():
                         lib.simt_b200_profile_enable(0)
                         k_ms = kms / n
                         nbytes = (1 if cols == 1 else 2) * npx
-                        out["hist"].append(dict(rows=rows, cols=cols, lut=use_lut, coherent=coherent, mode=mode,
+                        out["hist"].append(dict(rows=rows, cols=cols, lut=use_lut, coherent=str(coherent), mode=mode,
                                                 warps=warps, unroll=unroll, kernel_ms=k_ms, gbs=nbytes / k_ms / 1e6,
                                                 frac=nbytes / k_ms / 1e6 / PEAK, npx=npx))
                         print(out["hist"][-1], flush=True)

@@ -37,6 +37,11 @@ SIGNATURES = {
     "simt_class_hist": (c_int, [c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p]),
     "simt_label_map": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
     "simt_hist_set_tuning": (None, [c_int, c_int, c_int]),
+    "simt_t_regularizers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "simt_anchor_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "simt_bilinear_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                     c_void_p]),
 }
 OPTIONAL = set()
 

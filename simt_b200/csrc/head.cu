@@ -62,7 +62,7 @@ struct HeadArgs {
   float gscale;
   float* dlogits;
   unsigned long long* counter;  // dynamic unit scheduler (zero on entry; finalize re-zeroes it)
-  double* part_dT;      // [grid][C*CKP]
+  float* part_dT;       // [grid][C*CKP] per-CTA dT tiles (zero on entry; finalize re-zeroes them)
   double* part_loss;    // [grid]
   long long* part_cnt;  // [grid]
   int* err;
@@ -123,52 +123,6 @@ __device__ __forceinline__ float group_max(float v, unsigned gmask) {
   if (LPR >= 2) v = fmaxf(v, __shfl_xor_sync(gmask, v, 1));
   if (LPR >= 4) v = fmaxf(v, __shfl_xor_sync(gmask, v, 2));
   return v;
-}
-
-// Warp-collective flush of the per-thread dT accumulators D[] (column `old` of dT) into the
-// warp's PRIVATE fp64 shared tile wt[y][k].  Called with the whole warp converged.  Lanes with
-// the same label are summed with a shuffle tree and written by one lane per channel slice (plain
-// read-modify-write: nobody else touches this warp's tile) -- float/double atomicAdd on shared
-// memory is a CAS loop on sm_100 and collapses when a whole warp flushes the same hot class.
-// More than two distinct labels in one flush (incoherent label maps) fall back to the CAS path,
-// where the contention is spread over many addresses anyway.
-template <int CPL, int LPR>
-__device__ __forceinline__ void warp_flush_dT(float (&D)[CPL], int old, bool need, double* wt, int CKP, int CK,
-                                              int kbase, int lane) {
-  unsigned m = __ballot_sync(0xffffffffu, need);
-#pragma unroll 1
-  for (int round = 0; m != 0u && round < 2; ++round) {
-    const int src = __ffs(m) - 1;
-    const int lab = __shfl_sync(0xffffffffu, old, src);
-    const bool mine = need && old == lab;
-    const unsigned grp = __ballot_sync(0xffffffffu, mine);
-    float tot[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      float v = mine ? D[j] : 0.f;
-#pragma unroll
-      for (int o = 16; o >= LPR; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      tot[j] = v;
-      if (mine) D[j] = 0.f;
-    }
-    if (lane < LPR) {  // lane `sub` writes its channel slice
-      double* dst = wt + lab * CKP + kbase;
-#pragma unroll
-      for (int j = 0; j < CPL; ++j)
-        if (kbase + j < CK) dst[j] += (double)tot[j];
-    }
-    if (mine) need = false;
-    m &= ~grp;
-    __syncwarp();
-  }
-  if (need) {
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      if (kbase + j < CK) atomicAdd(&wt[old * CKP + kbase + j], (double)D[j]);
-      D[j] = 0.f;
-    }
-  }
-  __syncwarp();
 }
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2: two fp32 lanes per issue slot) ----
@@ -290,8 +244,6 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   // [NW][4][NP][32] float2: the cell corners of every lane (log2 domain), re-read once per pixel row
   float2* Lsm = reinterpret_cast<float2*>(smem_raw);
   unsigned char* sp = smem_raw + (size_t)NW * 4 * NP * 32 * sizeof(float2);
-  double* tiles = reinterpret_cast<double*>(sp);                      // [NW][C*CKP] dT tiles (BWD)
-  sp += BWD ? (size_t)NW * C * CKP * 8 : 0;
   float* Ts = reinterpret_cast<float*>(sp);                           // [C][CKP] = -T^T
   sp += (size_t)C * CKP * 4;
   float* Esm = reinterpret_cast<float*>(sp);                          // [NW][kEdgeRows][CKP + 1] edge column (BWD)
@@ -313,18 +265,16 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   float2* Lw = Lsm + (size_t)(tid >> 5) * 4 * NP * 32 + lane;  // + (arr * NP + q) * 32
   float* Ew = Esm + (size_t)(tid >> 5) * kEdgeRows * (CKP + 1);
 
-  // ---- one-time per CTA: -T transposed ([y][k], zero padded), dT tiles, pixel/cell tables ----
+  // ---- one-time per CTA: -T transposed ([y][k], zero padded), pixel/cell tables ----
   for (int i = tid; i < C * CKP; i += NT) {
     int y = i / CKP, k = i - y * CKP;
     float v = 0.f;
     if (k < CK) v = A.T ? __ldg(A.T + (size_t)k * C + y) : (k == y ? 1.f : 0.f);
     Ts[i] = -v;
   }
-  if (BWD)
-    for (int i = tid; i < NW * C * CKP; i += NT) tiles[i] = 0.0;
   for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
   for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
-  double* wt = tiles + (size_t)(tid >> 5) * C * CKP;
+  float* ct = A.part_dT + (size_t)blockIdx.x * C * CKP;  // this CTA's dT tile in global memory (L2 resident)
   __syncthreads();
 
   float2 D2[NP];     // dT accumulators (p_k / q) for the thread's current label column
@@ -347,11 +297,13 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #pragma unroll
     for (int q = 0; q < NP; ++q) nTc[q] = src[q];
   };
-  auto flush_lane = [&]() {  // per-lane flush (label change inside a run; rare on coherent maps)
+  // Hand the lane's dT accumulators (column `cur`) to the CTA tile: native red.global.add.f32, fire and
+  // forget (shared-memory float atomics are CAS loops on sm_100 and need warp-collective workarounds).
+  auto flush_lane = [&]() {
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const float v = (j & 1) ? D2[j >> 1].y : D2[j >> 1].x;
-      if (kbase + j < CK) atomicAdd(&wt[cur * CKP + kbase + j], (double)v);
+      if (kbase + j < CK) atomicAdd(&ct[cur * CKP + kbase + j], v);
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) D2[q] = make_float2(0.f, 0.f);
@@ -441,16 +393,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
             bad_label = true;  // neither a class nor the ignore label
           }
         }
-        {
-          // Row boundary, warp converged: if the row's label differs from the column the D[] accumulators
-          // belong to, flush them collectively before switching column.
-          const bool sw = first_lab >= 0 && first_lab != cur;
-          if (BWD) {
-            const bool need = sw && cur >= 0;
-            if (__any_sync(0xffffffffu, need))
-              warp_flush_dT<CPL, LPR>(reinterpret_cast<float(&)[CPL]>(D2), cur, need, wt, CKP, CK, kbase, lane);
-          }
-          if (sw) switch_column(first_lab);
+        if (first_lab >= 0 && first_lab != cur) {  // per lane: no collective needed
+          if (BWD && cur >= 0) flush_lane();
+          switch_column(first_lab);
         }
         float2 Gs[NP], G1[NP];
         if (BWD) {
@@ -483,7 +428,17 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // channel pairs packed into fp32x2 instructions).  WARP-UNIFORM: lane groups exchange partial
           // sums with full-mask shuffles, so invalid lanes/pixels are predicated off (w0/w1), never
           // branched around.
-          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1) {
+          // `mixed`: pixel 1 may belong to another label column than pixel 0 (c1 != cur)
+          auto body = [&](auto check_underflow, auto mixed, const float lam0, const float lam1, const bool w0,
+                          const bool w1, const int c1) {
+            constexpr bool MIXED = decltype(mixed)::value;
+            const bool diff1 = MIXED && w1 && c1 != cur;
+            float2 nT1[MIXED ? NP : 1];
+            if (MIXED) {
+              const float2* src1 = reinterpret_cast<const float2*>(Ts + (diff1 ? c1 : 0) * CKP + kbase);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) nT1[MIXED ? q : 0] = diff1 ? src1[q] : nTc[q];
+            }
             const float2 L0 = bcast2(lam0), L1 = bcast2(lam1);
             float2 e0[NP], e1[NP];
             float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0, ns0 = sum0, ns1 = sum0;
@@ -496,7 +451,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               sum0 = fadd2(sum0, e0[q]);
               sum1 = fadd2(sum1, e1[q]);
               ns0 = ffma2(e0[q], nTc[q], ns0);
-              ns1 = ffma2(e1[q], nTc[q], ns1);
+              ns1 = ffma2(e1[q], MIXED ? nT1[MIXED ? q : 0] : nTc[q], ns1);
             }
             float su0 = group_sum<LPR>(sum0.x + sum0.y, 0xffffffffu);
             float su1 = group_sum<LPR>(sum1.x + sum1.y, 0xffffffffu);
@@ -522,7 +477,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 su0 += e0[q].x + e0[q].y;
                 su1 += e1[q].x + e1[q].y;
                 s0 -= e0[q].x * nTc[q].x + e0[q].y * nTc[q].y;
-                s1 -= e1[q].x * nTc[q].x + e1[q].y * nTc[q].y;
+                const float2 tq1 = MIXED ? nT1[MIXED ? q : 0] : nTc[q];
+                s1 -= e1[q].x * tq1.x + e1[q].y * tq1.y;
               }
               su0 = group_sum<LPR>(su0, 0xffffffffu);
               su1 = group_sum<LPR>(su1, 0xffffffffu);
@@ -550,15 +506,21 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #pragma unroll
               for (int q = 0; q < NP; ++q) {
                 // c = (p_k - p_k T_ky / q) / e_k = rs - T_ky * is ;  c1 = lambda * c
-                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(nTc[q], I1, R1);
-                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(nTc[q], LI1, LR1);
+                const float2 tq1 = MIXED ? nT1[MIXED ? q : 0] : nTc[q];
+                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(tq1, I1, R1);
+                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(tq1, LI1, LR1);
                 Gs[q] = ffma2(e0[q], ca, Gs[q]);
                 Gs[q] = ffma2(e1[q], cb, Gs[q]);
                 G1[q] = ffma2(e0[q], c1a, G1[q]);
                 G1[q] = ffma2(e1[q], c1b, G1[q]);
-                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q
-                D2[q] = ffma2(e1[q], I1, D2[q]);
+                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q, column `cur`
               }
+              if (diff1) {  // pixel 1 starts a new label column
+                if (cur >= 0) flush_lane();
+                switch_column(c1);
+              }
+#pragma unroll
+              for (int q = 0; q < NP; ++q) D2[q] = ffma2(e1[q], I1, D2[q]);
             }
           };
 
@@ -574,11 +536,13 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 const unsigned c1 = (unsigned)(codes >> (16 * st + 8)) & 0xffu;
                 const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
                 const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
-                body(std::false_type{}, lambda_of(xa + 2 * st, A.sx, cx), lambda_of(xa + 2 * st + 1, A.sx, cx), v0, v1);
+                body(std::false_type{}, std::false_type{}, lambda_of(xa + 2 * st, A.sx, cx),
+                     lambda_of(xa + 2 * st + 1, A.sx, cx), v0, v1, 0);
               }
             }
           } else {
-            // ---- generic row: label changes inside a run, long runs, or extreme logit range ----
+            // ---- generic row: label changes inside a run, long runs, or extreme logit range: the same
+            // 2-pixel step with a per-pixel label column and the softmax underflow check ----
 #pragma unroll 1
             for (int i = 0; i < nmax; i += 2) {
               unsigned c0, c1;
@@ -594,25 +558,12 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               }
               const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
               const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
-              const bool same = (!v0 || (int)c0 == cur) && (!v1 || (int)c1 == cur);
-              const float lam0 = lambda_of(xa + i, A.sx, cx);
-              const float lam1 = lambda_of(xa + i + 1, A.sx, cx);
-              if (__all_sync(0xffffffffu, same)) {
-                body(std::true_type{}, lam0, lam1, v0, v1);
-              } else {
-                // some lane crosses a label boundary inside its run: one pixel at a time, with a
-                // per-lane column switch in between (still warp-uniform control flow)
-#pragma unroll 1
-                for (int rep = 0; rep < 2; ++rep) {
-                  const unsigned cc = rep ? c1 : c0;
-                  const bool wv = rep ? v1 : v0;
-                  if (wv && (int)cc != cur) {
-                    if (BWD && cur >= 0) flush_lane();
-                    switch_column((int)cc);
-                  }
-                  body(std::true_type{}, rep ? lam1 : lam0, 0.f, wv, false);
-                }
+              if (v0 && (int)c0 != cur) {  // per lane; no shuffles inside
+                if (BWD && cur >= 0) flush_lane();
+                switch_column((int)c0);
               }
+              body(std::true_type{}, std::true_type{}, lambda_of(xa + i, A.sx, cx), lambda_of(xa + i + 1, A.sx, cx), v0,
+                   v1, (int)c1);
             }
           }
         }
@@ -689,14 +640,12 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
       }
     }  // cell-rows of the unit
 
-    // per-unit hand-off: fp32 partials of a unit are summed in a fixed order; across units in fp64
-    if (BWD)
-      warp_flush_dT<CPL, LPR>(reinterpret_cast<float(&)[CPL]>(D2), cur, cur >= 0, wt, CKP, CK, kbase, lane);
     loss_d += (double)loss_acc;
     unit = next_unit;
   }
 
   // ---- CTA epilogue: partials ---------------------------------------------------------------
+  if (BWD && cur >= 0) flush_lane();
   if (bad_label) atomicOr(A.err, SIMT_ERRBIT_LABEL_RANGE);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -712,47 +661,56 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     A.part_loss[blockIdx.x] = tl;
     A.part_cnt[blockIdx.x] = tc;
   }
-  if (BWD) {
-    double* pd = A.part_dT + (size_t)blockIdx.x * C * CKP;
-    for (int i = tid; i < C * CKP; i += NT) {
-      double v = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < NW; ++wv) v += tiles[(size_t)wv * C * CKP + i];
-      pd[i] = v;
-    }
-  }
 }
 
-// One warp per output: outputs 0 .. C*CKP-1 are dT entries ([y][k] layout of the partials),
-// then loss and count.  Fixed summation order over the CTA partials.
+// Fixed-order reduction of the per-CTA partials.  blockDim = (32 outputs, 8 slices of the CTA range):
+// consecutive threads read consecutive tile entries (coalesced), every slice sums its CTAs in order and
+// the 8 slice sums are added in order.  The tiles are re-zeroed for the next call on the way.  The last
+// block reduces loss / count and re-arms the unit scheduler.
 __global__ void __launch_bounds__(256) head_finalize_kernel(
-    const double* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
+    float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
     int nparts, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
     double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   const int ndt = C * CKP;
-  if (warp < ndt) {
-    const int y = warp / CKP, k = warp - y * CKP;
-    if (k >= CK) return;
-    double s = 0;
-    if (mode != MODE_FWD)
-      for (int g = lane; g < nparts; g += 32) s += part_dT[(size_t)g * ndt + warp];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      if (stats) stats[2 + k * C + y] = -s;
-      if (dT_out) dT_out[k * C + y] = (float)(-s * (double)gscale);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ double sm[8][33];
+  __shared__ long long smi[8];
+  if ((int)blockIdx.x < (int)gridDim.x - 1) {
+    const int o = blockIdx.x * 32 + tx;  // output index in the [y][k] layout of the tiles
+    double s = 0.0;
+    if (o < ndt && mode != MODE_FWD) {
+      for (int g = ty; g < nparts; g += 8) {
+        float* p = part_dT + (size_t)g * ndt + o;
+        s += (double)*p;
+        *p = 0.f;
+      }
     }
-  } else if (warp == ndt) {
-    double l = 0; long long c = 0;
-    for (int g = lane; g < nparts; g += 32) { l += part_loss[g]; c += part_cnt[g]; }
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && o < ndt) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += sm[q][tx];
+      const int y = o / CKP, k = o - y * CKP;
+      if (k < CK) {
+        if (stats) stats[2 + k * C + y] = -t;
+        if (dT_out) dT_out[k * C + y] = (float)(-t * (double)gscale);
+      }
+    }
+  } else {
+    double l = 0.0;
+    long long c = 0;
+    for (int g = threadIdx.x; g < nparts; g += 256) { l += part_loss[g]; c += part_cnt[g]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       l += __shfl_xor_sync(0xffffffffu, l, o);
       c += __shfl_xor_sync(0xffffffffu, c, o);
     }
-    if (lane == 0) {
+    if (tx == 0) { sm[ty][0] = l; smi[ty] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      l = 0.0; c = 0;
+      for (int q = 0; q < 8; ++q) { l += sm[q][0]; c += smi[q]; }
       *counter = 0ULL;  // the main kernel of this call has finished: re-arm the unit scheduler
       const double ls = -kLn2 * l;
       if (stats) { stats[0] = ls; stats[1] = (double)c; }
@@ -785,7 +743,7 @@ __global__ void head_scale_kernel(float* __restrict__ dlogits, long long n, cons
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f64 x G*C*CKPmax]
+// workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f32 x G*C*CKPmax]
 static constexpr int kMaxGridPerSm = 8;
 static constexpr int kMaxCKP = 64;
 
@@ -905,7 +863,7 @@ static int make_plan(int mode, int B, int CK, int C, int h, int w, int H, int W,
   A->nunits = (long long)B * A->units_y * A->units_x;
   const bool bwd = mode != MODE_FWD;
   const size_t nw = (size_t)(P->NT / 32);
-  P->smem = nw * 4 * (P->CPL / 2) * 32 * 8 + (bwd ? nw * C * P->CKP * 8 : 0) + (size_t)C * P->CKP * 4 +
+  P->smem = nw * 4 * (P->CPL / 2) * 32 * 8 + (size_t)C * P->CKP * 4 +
             (bwd ? nw * kEdgeRows * (P->CKP + 1) * 4 : 0) + (size_t)(A->ncx + A->ncy + 2) * 4;
   return 0;
 }
@@ -946,14 +904,13 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   A.counter = reinterpret_cast<unsigned long long*>(ws);
   A.part_loss = reinterpret_cast<double*>(ws + 64);
   A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
-  A.part_dT = reinterpret_cast<double*>(ws + 64 + G * 16);
+  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
   if (mode != MODE_FWD)
     SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
   int grid = 0;
   rc = dispatch_all(mode, label_bytes, A, P, st, &grid);
   if (rc) return rc;
-  const int nwarps = C * P.CKP + 1;
-  const int fgrid = (nwarps * 32 + 255) / 256;
+  const int fgrid = (C * P.CKP + 31) / 32 + 1;
   head_finalize_kernel<<<fgrid, 256, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, mode, gscale,
                                               A.counter, stats, loss_mean, dT_out, err_flag);
   return (int)cudaGetLastError();

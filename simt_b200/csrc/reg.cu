@@ -134,68 +134,98 @@ __global__ void __launch_bounds__(256) t_reg_kernel(const float* __restrict__ T,
 // anchor statistics
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pack_max(float v, long long idx) {
-  // monotone float -> uint, high 32 bits; low 32 bits = ~idx so that the SMALLEST index wins ties
+  // monotone float -> uint in the high 32 bits; low 32 bits = ~idx so that the SMALLEST index wins ties
   unsigned u = __float_as_uint(v);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
 }
 
-template <int MAXCK>
-__global__ void __launch_bounds__(256) anchor_stats_kernel(const float* __restrict__ logits, int B, int CK, int h,
-                                                            int w, int H, int W, float sy, float sx,
-                                                            unsigned long long* __restrict__ packed /*[CK]*/,
-                                                            unsigned long long* __restrict__ exist) {
-  // one thread per output pixel (grid-stride); values follow torch's formula
-  //   w0h*(w0w*x00 + w1w*x01) + w1h*(w0w*x10 + w1w*x11)
-  __shared__ unsigned long long s_best[MAXCK];
-  __shared__ unsigned long long s_exist;
-  for (int k = threadIdx.x; k < CK; k += blockDim.x) s_best[k] = 0ull;
-  if (threadIdx.x == 0) s_exist = 0ull;
-  __syncthreads();
+struct Bilin {
+  int o00, o01, o10, o11;
+  float ly0, ly1, lx0, lx1;
+};
+// torch's align_corners=True source index / lambda arithmetic (UpSample.h), unfused
+__device__ __forceinline__ Bilin bilin_setup(int Y, int X, int h, int w, float sy, float sx) {
+  const float fy = __fmul_rn(sy, (float)Y), fx = __fmul_rn(sx, (float)X);
+  const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+  const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+  Bilin b;
+  b.ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f);
+  b.lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+  b.ly0 = 1.f - b.ly1;
+  b.lx0 = 1.f - b.lx1;
+  b.o00 = y0 * w + x0; b.o01 = y0 * w + x1; b.o10 = y1 * w + x0; b.o11 = y1 * w + x1;
+  return b;
+}
+__device__ __forceinline__ float bilin_eval(const float* __restrict__ pl, const Bilin& b) {
+  // w0h*(w0w*x00 + w1w*x01) + w1h*(w0w*x10 + w1w*x11), every product and sum rounded
+  const float top = __fadd_rn(__fmul_rn(b.lx0, __ldg(pl + b.o00)), __fmul_rn(b.lx1, __ldg(pl + b.o01)));
+  const float bot = __fadd_rn(__fmul_rn(b.lx0, __ldg(pl + b.o10)), __fmul_rn(b.lx1, __ldg(pl + b.o11)));
+  return __fadd_rn(__fmul_rn(b.ly0, top), __fmul_rn(b.ly1, bot));
+}
+
+// (A) per channel: arg-max pixel of the upsampled logit.  grid = (blocks, CK)
+__global__ void __launch_bounds__(256) anchor_channel_max_kernel(const float* __restrict__ logits, int B, int CK, int h,
+                                                                  int w, int H, int W, float sy, float sx,
+                                                                  unsigned long long* __restrict__ packed) {
+  const int k = blockIdx.y;
   const long long npix = (long long)B * H * W;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  unsigned long long my_exist = 0ull;
+  unsigned long long best = 0ull;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
     const int X = (int)(p % W);
     const long long t = p / W;
     const int Y = (int)(t % H);
     const int b = (int)(t / H);
-    const float fy = __fmul_rn(sy, (float)Y), fx = __fmul_rn(sx, (float)X);
-    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
-    const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
-    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const Bilin bl = bilin_setup(Y, X, h, w, sy, sx);
+    const float z = bilin_eval(logits + ((size_t)b * CK + k) * h * w, bl);
+    const unsigned long long pk = pack_max(z, p);
+    best = pk > best ? pk : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  __shared__ unsigned long long sb[8];
+  if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) best = sb[i] > best ? sb[i] : best;
+    if (best) atomicMax(&packed[k], best);
+  }
+}
+
+// (B) per pixel: arg-max class (lowest class wins ties) -> presence bit mask
+__global__ void __launch_bounds__(256) anchor_exist_kernel(const float* __restrict__ logits, int B, int CK, int h, int w,
+                                                            int H, int W, float sy, float sx,
+                                                            unsigned long long* __restrict__ exist) {
+  const long long npix = (long long)B * H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long mine = 0ull;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const int X = (int)(p % W);
+    const long long t = p / W;
+    const int Y = (int)(t % H);
+    const int b = (int)(t / H);
+    const Bilin bl = bilin_setup(Y, X, h, w, sy, sx);
     const float* base = logits + (size_t)b * CK * h * w;
     float best = -INFINITY;
     int bestk = 0;
     for (int k = 0; k < CK; ++k) {
-      const float* pl = base + (size_t)k * h * w;
-      const float v00 = __ldg(pl + y0 * w + x0), v01 = __ldg(pl + y0 * w + x1);
-      const float v10 = __ldg(pl + y1 * w + x0), v11 = __ldg(pl + y1 * w + x1);
-      const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
-      const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
-      const float z = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-      if (z > best) { best = z; bestk = k; }
-      // per-channel arg-max over pixels: warp-aggregate, then one shared atomicMax per warp
-      unsigned long long pk = pack_max(z, p);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(__activemask(), pk, o);
-        pk = other > pk ? other : pk;
-      }
-      if ((threadIdx.x & 31) == 0 || true) {
-        if (pk > s_best[k] && pack_max(z, p) == pk) atomicMax(&s_best[k], pk);
-      }
+      const float z = bilin_eval(base + (size_t)k * h * w, bl);
+      if (z > best || k == 0) { best = z; bestk = k; }
     }
-    my_exist |= 1ull << bestk;
+    mine |= 1ull << bestk;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) my_exist |= __shfl_xor_sync(0xffffffffu, my_exist, o);
-  if ((threadIdx.x & 31) == 0) atomicOr(&s_exist, my_exist);
+  for (int o = 16; o > 0; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
+  __shared__ unsigned long long se;
+  if (threadIdx.x == 0) se = 0ull;
   __syncthreads();
-  for (int k = threadIdx.x; k < CK; k += blockDim.x)
-    if (s_best[k]) atomicMax(&packed[k], s_best[k]);
-  if (threadIdx.x == 0 && s_exist) atomicOr(exist, s_exist);
+  if ((threadIdx.x & 31) == 0 && mine) atomicOr(&se, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && se) atomicOr(exist, se);
 }
 
 __global__ void anchor_unpack_kernel(const unsigned long long* __restrict__ packed, int CK,
@@ -207,6 +237,21 @@ __global__ void anchor_unpack_kernel(const unsigned long long* __restrict__ pack
   unsigned u = (unsigned)(pk >> 32);
   u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
   if (anchor_val) anchor_val[k] = __uint_as_float(u);
+}
+
+// rows[r][c] = bilinear sample of src[b, c] at flat pixel idx[r]  (labelC_flat[Anchor_index], trainV2_simt.py:378)
+__global__ void bilinear_gather_kernel(const float* __restrict__ src, int B, int C, int h, int w, int H, int W, float sy,
+                                       float sx, const long long* __restrict__ idx, int n, float* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  const int r = i / C, c = i - r * C;
+  const long long p = idx[r];
+  const int X = (int)(p % W);
+  const long long t = p / W;
+  const int Y = (int)(t % H);
+  const int b = (int)(t / H);
+  const Bilin bl = bilin_setup(Y, X, h, w, sy, sx);
+  rows[i] = bilin_eval(src + ((size_t)b * C + c) * h * w, bl);
 }
 
 }  // namespace simt
@@ -244,11 +289,28 @@ int simt_anchor_stats(const float* logits, int B, int CK, int h, int w, int H, i
   SIMT_CUDA_TRY(cudaMemsetAsync(exist_mask, 0, sizeof(unsigned long long), st));
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  long long grid = ((long long)B * H * W + 255) / 256;
-  if (grid > (long long)di.sm_count * 8) grid = (long long)di.sm_count * 8;
-  anchor_stats_kernel<64><<<(int)grid, 256, 0, st>>>(logits, B, CK, h, w, H, W, sy, sx, scratch, exist_mask);
+  const long long npix = (long long)B * H * W;
+  long long gx = (npix + 256 * 8 - 1) / (256 * 8);
+  if (gx > (long long)di.sm_count * 2) gx = (long long)di.sm_count * 2;
+  if (gx < 1) gx = 1;
+  anchor_channel_max_kernel<<<dim3((unsigned)gx, (unsigned)CK), 256, 0, st>>>(logits, B, CK, h, w, H, W, sy, sx, scratch);
+  SIMT_CUDA_TRY(cudaGetLastError());
+  long long ge = (npix + 255) / 256;
+  if (ge > (long long)di.sm_count * 8) ge = (long long)di.sm_count * 8;
+  anchor_exist_kernel<<<(int)ge, 256, 0, st>>>(logits, B, CK, h, w, H, W, sy, sx, exist_mask);
   SIMT_CUDA_TRY(cudaGetLastError());
   anchor_unpack_kernel<<<1, 64, 0, st>>>(scratch, CK, anchor_idx, anchor_val);
+  return (int)cudaGetLastError();
+}
+
+int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, int W, const long long* pixel_idx, int n,
+                         float* rows, void* stream) {
+  if (!src || !pixel_idx || !rows || B <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || n < 0) return SIMT_EINVAL;
+  if (n == 0) return 0;
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  bilinear_gather_kernel<<<(n * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, B, C, h, w, H, W, sy, sx, pixel_idx, n,
+                                                                                rows);
   return (int)cudaGetLastError();
 }
 
