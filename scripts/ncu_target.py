@@ -19,7 +19,8 @@ if what == "head":
     K = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     coh = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
     cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
-    lg, lab = O.synth_head_inputs(B, 19 + K, 65, 129, 512, 1024, seed=1234, coherent=coh, class_dist=cd)
+    lg, lab = O.synth_head_inputs(B, 19 + K, 65, 129, 512, 1024, seed=1234, coherent=coh, class_dist=cd,
+                                   block=(36, 52))   # bench.py's label pattern
     lg, lab = lg.to(dev), lab.to(dev)
     torch.manual_seed(1234)
     T = simt_b200.sig_NTM(19, K).to(dev)().detach()
@@ -35,7 +36,7 @@ else:
     coh = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
     gts, prs = [], []
     for i in range(8):
-        gt, pr = O.synth_eval_pair(1024, 2048, seed=i, coherent=coh)
+        gt, pr = O.synth_eval_pair(1024, 2048, seed=i, coherent=coh, block=(96, 160), noise=0.0)
         gts.append(torch.from_numpy(gt)); prs.append(torch.from_numpy(pr))
     gt = torch.stack(gts).repeat(nimg // 8, 1, 1).to(dev)
     pr = torch.stack(prs).repeat(nimg // 8, 1, 1).to(dev)

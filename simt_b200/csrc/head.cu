@@ -126,27 +126,34 @@ __device__ __forceinline__ float group_max(float v, unsigned gmask) {
 }
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2: two fp32 lanes per issue slot) ----
+// Operands are packed/unpacked with mov.b64 {lo, hi} inside the asm block (ptxas folds these into
+// register-pair allocation); reinterpret_cast of float2 references forces the values through local memory.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(r)
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
-        "l"(reinterpret_cast<unsigned long long&>(c)));
-  return reinterpret_cast<float2&>(r);
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
 }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;"
-      : "=l"(r)
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return reinterpret_cast<float2&>(r);
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
 }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;"
-      : "=l"(r)
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return reinterpret_cast<float2&>(r);
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
 }
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 
@@ -469,8 +476,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               tm0 = group_max<LPR>(tm0, 0xffffffffu);
               tm1 = group_max<LPR>(tm1, 0xffffffffu);
               su0 = su1 = s0 = s1 = 0.f;
-#pragma unroll 1
-              for (int q = 0; q < NP; ++q) {
+#pragma unroll
+              for (int q = 0; q < NP; ++q) {  // (static indices only: a dynamic q would push the arrays to local memory)
                 const float2 t0 = ffma2(L0, d[q], a[q]), t1 = ffma2(L1, d[q], a[q]);
                 e0[q] = make_float2(ex2_approx(t0.x - tm0), ex2_approx(t0.y - tm0));
                 e1[q] = make_float2(ex2_approx(t1.x - tm1), ex2_approx(t1.y - tm1));
