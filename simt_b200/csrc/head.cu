@@ -57,6 +57,7 @@ struct HeadArgs {
   float sy, sx;    // torch's align_corners scales (float)(in-1)/(out-1)
   int ncy, ncx;    // number of cells = max(in-1, 1)
   int ur;          // cell-rows per unit
+  int rs;          // a cell-row's pixel rows are split over rs units (only with ur == 1): finer tail
   int units_y, units_x;
   long long nunits;
   float gscale;
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     const int per_img = A.units_y * A.units_x;
     const int b = (int)(unit / per_img);
     const int urem = (int)(unit - (long long)b * per_img);
-    const int uy = urem / A.units_x, ux = urem - uy * A.units_x;
+    const int uyr = urem / A.units_x, ux = urem - uyr * A.units_x;
+    const int uy = uyr / A.rs, part = uyr - uy * A.rs;   // units_y counts (cell-row group, row part) pairs
     const int cx = ux * CPW + pidx;
     const bool cell_ok = cx < A.ncx;
     const int xa = cell_ok ? xs_tab[cx] : 0;
@@ -333,18 +335,36 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     const int gx0 = min(cx, w - 1), gx1 = min(cx + 1, w - 1);
     const int edge_gx = min(ux * CPW + ncell_u, w - 1);          // node column right of the unit
     float loss_acc = 0.f;
+    if (next_unit < A.nunits) {
+      // pull the next unit's corner logits (and its first label row) towards L2 while this unit computes
+      const int nb = (int)(next_unit / per_img);
+      const int nrem = (int)(next_unit - (long long)nb * per_img);
+      const int nuy = (nrem / A.units_x) / A.rs, nux = nrem - (nrem / A.units_x) * A.units_x;
+      const int ncx = min(nux * CPW + pidx, A.ncx - 1), ncy0 = nuy * A.ur;
+      const float* np0 = A.logits + (((size_t)nb * CK + kbase) * h + min(ncy0, h - 1)) * w + min(ncx, w - 1);
+#pragma unroll
+      for (int j = 0; j < CPL; j += 2)   // one 128-byte line usually covers a node pair and its neighbours
+        if (kbase + j < CK) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np0 + (size_t)j * h * w));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np0 + (size_t)j * h * w + w));
+        }
+      if (sub == 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + ((long long)nb * A.H + ys_tab[ncy0]) * A.W + xs_tab[ncx]));
+    }
 
     const int cy_begin = uy * A.ur, cy_end = min(A.ncy, (uy + 1) * A.ur);
-    const int Yfirst = ys_tab[cy_begin];
-    const int Ylast = ys_tab[cy_end];  // one past the unit's last pixel row
+    // this unit's pixel rows: all rows of its cell-rows, or the part-th slice of the single cell-row
+    const int Yall0 = ys_tab[cy_begin], Yall1 = ys_tab[cy_end];
+    const int Yfirst = Yall0 + (int)(((long long)(Yall1 - Yall0) * part) / A.rs);
+    const int Ylast = Yall0 + (int)(((long long)(Yall1 - Yall0) * (part + 1)) / A.rs);  // one past the last row
     RawRun raw_next = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u};
     if (Yfirst < Ylast)
       raw_next = LabelFetch<LabelT>::issue(labels, ((long long)b * A.H + Yfirst) * A.W + xa, nrun, labels_end,
                                            A.label_words_ok != 0, A.ignore, C);
 
     for (int cy = cy_begin; cy < cy_end; ++cy) {
-      const int Y0 = ys_tab[cy];
-      const int Y1 = ys_tab[cy + 1];
+      const int Y0 = max(ys_tab[cy], Yfirst);
+      const int Y1 = min(ys_tab[cy + 1], Ylast);
       if (Y1 <= Y0) continue;  // warp-uniform
       const int gy0 = min(cy, h - 1), gy1 = min(cy + 1, h - 1);
       const bool edge_smem = BWD && (Y1 - Y0 <= kEdgeRows);
@@ -386,24 +406,6 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
         if (Y + 1 < Ylast)  // next row's labels are in flight during this row's arithmetic
           raw_next = LabelFetch<LabelT>::issue(labels, rowbase + A.W, nrun, labels_end, A.label_words_ok != 0,
                                                A.ignore, C);
-        // ---- classify the row's (up to 8) labels: first valid label, label-uniform?, contract check ----
-        int first_lab = -1;
-        bool row_uni = true;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = (int)((codes >> (8 * q)) & 0xffu);
-          const bool valid = c < C && c != ign8;
-          if (valid) {
-            if (first_lab < 0) first_lab = c;
-            row_uni = row_uni && (c == first_lab);
-          } else if (c != ign8 && q < nrun) {
-            bad_label = true;  // neither a class nor the ignore label
-          }
-        }
-        if (first_lab >= 0 && first_lab != cur) {  // per lane: no collective needed
-          if (BWD && cur >= 0) flush_lane();
-          switch_column(first_lab);
-        }
         float2 Gs[NP], G1[NP];
         if (BWD) {
 #pragma unroll
@@ -435,17 +437,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // channel pairs packed into fp32x2 instructions).  WARP-UNIFORM: lane groups exchange partial
           // sums with full-mask shuffles, so invalid lanes/pixels are predicated off (w0/w1), never
           // branched around.
-          // `mixed`: pixel 1 may belong to another label column than pixel 0 (c1 != cur)
-          auto body = [&](auto check_underflow, auto mixed, const float lam0, const float lam1, const bool w0,
-                          const bool w1, const int c1) {
-            constexpr bool MIXED = decltype(mixed)::value;
-            const bool diff1 = MIXED && w1 && c1 != cur;
-            float2 nT1[MIXED ? NP : 1];
-            if (MIXED) {
-              const float2* src1 = reinterpret_cast<const float2*>(Ts + (diff1 ? c1 : 0) * CKP + kbase);
-#pragma unroll
-              for (int q = 0; q < NP; ++q) nT1[MIXED ? q : 0] = diff1 ? src1[q] : nTc[q];
-            }
+          // both pixels of a step belong to the lane's current label column `cur`
+          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1) {
             const float2 L0 = bcast2(lam0), L1 = bcast2(lam1);
             float2 e0[NP], e1[NP];
             float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0, ns0 = sum0, ns1 = sum0;
@@ -458,7 +451,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               sum0 = fadd2(sum0, e0[q]);
               sum1 = fadd2(sum1, e1[q]);
               ns0 = ffma2(e0[q], nTc[q], ns0);
-              ns1 = ffma2(e1[q], MIXED ? nT1[MIXED ? q : 0] : nTc[q], ns1);
+              ns1 = ffma2(e1[q], nTc[q], ns1);
             }
             float su0 = group_sum<LPR>(sum0.x + sum0.y, 0xffffffffu);
             float su1 = group_sum<LPR>(sum1.x + sum1.y, 0xffffffffu);
@@ -484,8 +477,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 su0 += e0[q].x + e0[q].y;
                 su1 += e1[q].x + e1[q].y;
                 s0 -= e0[q].x * nTc[q].x + e0[q].y * nTc[q].y;
-                const float2 tq1 = MIXED ? nT1[MIXED ? q : 0] : nTc[q];
-                s1 -= e1[q].x * tq1.x + e1[q].y * tq1.y;
+                s1 -= e1[q].x * nTc[q].x + e1[q].y * nTc[q].y;
               }
               su0 = group_sum<LPR>(su0, 0xffffffffu);
               su1 = group_sum<LPR>(su1, 0xffffffffu);
@@ -513,66 +505,53 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #pragma unroll
               for (int q = 0; q < NP; ++q) {
                 // c = (p_k - p_k T_ky / q) / e_k = rs - T_ky * is ;  c1 = lambda * c
-                const float2 tq1 = MIXED ? nT1[MIXED ? q : 0] : nTc[q];
-                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(tq1, I1, R1);
-                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(tq1, LI1, LR1);
+                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(nTc[q], I1, R1);
+                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(nTc[q], LI1, LR1);
                 Gs[q] = ffma2(e0[q], ca, Gs[q]);
                 Gs[q] = ffma2(e1[q], cb, Gs[q]);
                 G1[q] = ffma2(e0[q], c1a, G1[q]);
                 G1[q] = ffma2(e1[q], c1b, G1[q]);
-                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q, column `cur`
+                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q
+                D2[q] = ffma2(e1[q], I1, D2[q]);
               }
-              if (diff1) {  // pixel 1 starts a new label column
-                if (cur >= 0) flush_lane();
-                switch_column(c1);
-              }
-#pragma unroll
-              for (int q = 0; q < NP; ++q) D2[q] = ffma2(e1[q], I1, D2[q]);
             }
           };
 
-          const bool fast_row = row_uni && range_safe;
-          if (nmax <= 8 && __all_sync(0xffffffffu, fast_row)) {
-            // ---- fast row: every lane's valid pixels carry the lane's current label and no pixel can
-            // underflow -> straight-line steps with no votes or branches; unrolled so that the next
-            // step's FFMA2/MUFU issue under the previous step's reduction tail
-#pragma unroll
-            for (int st = 0; st < 4; ++st) {
-              if (2 * st < nmax) {
-                const unsigned c0 = (unsigned)(codes >> (16 * st)) & 0xffu;
-                const unsigned c1 = (unsigned)(codes >> (16 * st + 8)) & 0xffu;
-                const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
-                const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
-                body(std::false_type{}, std::false_type{}, lambda_of(xa + 2 * st, A.sx, cx),
-                     lambda_of(xa + 2 * st + 1, A.sx, cx), v0, v1, 0);
-              }
-            }
-          } else {
-            // ---- generic row: label changes inside a run, long runs, or extreme logit range: the same
-            // 2-pixel step with a per-pixel label column and the softmax underflow check ----
-#pragma unroll 1
-            for (int i = 0; i < nmax; i += 2) {
+          // ---- the pixel loop: every lane walks its own run with a cursor `pos`, two pixels per step.
+          // A pair that straddles a label boundary is split (pixel 1 waits for the next step), so a step never
+          // mixes two T columns; the column switch itself is per lane and shuffle-free.  The loop is
+          // WARP-UNIFORM (vote on "anyone left"), lanes that are done run predicated-off steps.
+          auto run_row = [&](auto check_underflow) {
+            int pos = 0;
+            while (__any_sync(0xffffffffu, pos < nrun)) {
               unsigned c0, c1;
-              if (i < 8) {  // i is even, so i + 1 < 8 as well
-                c0 = (unsigned)(codes >> (8 * i)) & 0xffu;
-                c1 = (unsigned)(codes >> (8 * i + 8)) & 0xffu;
-              } else {
-                c0 = (i < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + i, A.ignore, C) : 0xffu;
-                c1 = (i + 1 < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + i + 1, A.ignore, C) : 0xffu;
-                if ((c0 >= (unsigned)C && (int)c0 != ign8 && i < nrun) ||
-                    (c1 >= (unsigned)C && (int)c1 != ign8 && i + 1 < nrun))
-                  bad_label = true;
+              if (pos < 7) {
+                const unsigned two = (unsigned)(codes >> (8 * pos));
+                c0 = two & 0xffu;
+                c1 = (two >> 8) & 0xffu;
+              } else {  // runs longer than the 8 prefetched labels (large up-sampling factors)
+                c0 = (pos < nrun) ? ((pos < 8) ? (unsigned)(codes >> 56) & 0xffu
+                                                : LabelFetch<LabelT>::one(labels, rowbase + pos, A.ignore, C)) : 0xffu;
+                c1 = (pos + 1 < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + pos + 1, A.ignore, C) : 0xffu;
               }
-              const bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
-              const bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
-              if (v0 && (int)c0 != cur) {  // per lane; no shuffles inside
+              bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
+              bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
+              if (!(v0 && v1)) {  // neither a class nor the ignore label (nor padding past the run)?
+                if ((!v0 && (int)c0 != ign8 && pos < nrun) || (!v1 && (int)c1 != ign8 && pos + 1 < nrun)) bad_label = true;
+              }
+              int adv = 2;
+              if (v0 && v1 && c0 != c1) { v1 = false; adv = 1; }  // label boundary inside the pair
+              const int lab = v0 ? (int)c0 : (int)c1;
+              if ((v0 || v1) && lab != cur) {
                 if (BWD && cur >= 0) flush_lane();
-                switch_column((int)c0);
+                switch_column(lab);
               }
-              body(std::true_type{}, std::true_type{}, lambda_of(xa + i, A.sx, cx), lambda_of(xa + i + 1, A.sx, cx), v0,
-                   v1, (int)c1);
+              body(check_underflow, lambda_of(xa + pos, A.sx, cx), lambda_of(xa + pos + 1, A.sx, cx), v0, v1);
+              pos += adv;
             }
-          }
+          };
+          if (__all_sync(0xffffffffu, range_safe)) run_row(std::false_type{});
+          else run_row(std::true_type{});
         }
         if (BWD) {
           // node column cx of this row = G0(cx) + G1(cx-1); the left neighbour is LPR lanes below
@@ -865,7 +844,20 @@ static int make_plan(int mode, int B, int CK, int C, int h, int w, int H, int W,
   }
   const int cpw = 32 / P->LPR;
   A->ur = ur;
-  A->units_y = (A->ncy + ur - 1) / ur;
+  // split each cell-row over rs units when the grid would otherwise see only a few units per warp
+  int rs = g_tuning.unused > 0 ? g_tuning.unused : 0;
+  if (rs <= 0) {
+    DeviceInfo di;
+    if (device_info(&di) == 0) {
+      const double warps = (double)di.sm_count * 3.0 * (P->NT / 32);   // ~3 CTAs per SM resident
+      const double base_units = (double)B * ((A->ncy + ur - 1) / ur) * ((A->ncx + cpw - 1) / cpw);
+      rs = (int)(4.0 * warps / base_units + 0.5);                      // aim at >= ~4 units per warp
+      if (rs > 4) rs = 4;
+    }
+  }
+  if (ur > 1) rs = 1;
+  A->rs = rs < 1 ? 1 : rs;
+  A->units_y = ((A->ncy + ur - 1) / ur) * A->rs;
   A->units_x = (A->ncx + cpw - 1) / cpw;
   A->nunits = (long long)B * A->units_y * A->units_x;
   const bool bwd = mode != MODE_FWD;
