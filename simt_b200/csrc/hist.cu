@@ -237,7 +237,7 @@ static int run_hist(const void* a, int a_bytes, const void* b, int b_bytes, long
       A.b = b ? static_cast<const uint8_t*>(b) + off : nullptr;
       A.n = len; A.lut = lut; A.n_rows = n_rows; A.n_cols = n_cols; A.nbins = (int)nbins;
       A.hist = h; A.err = err_flag;
-      int unroll = g_hist_tuning.unroll > 0 ? g_hist_tuning.unroll : 2;
+      int unroll = g_hist_tuning.unroll > 0 ? g_hist_tuning.unroll : 1;
       int warps = g_hist_tuning.warps > 0 ? g_hist_tuning.warps : 16;
       if (warps > 16) warps = 16;
       const size_t smem = 256 + (size_t)kRep * ((size_t)A.nbins | 1) * 4;   // <= 33 KB for 1024 bins
