@@ -3,7 +3,7 @@
 Host side mirrors the reference's Python call surface for this one path; the arithmetic is in
 hand-written CUDA behind a C ABI (include/simt_b200.h, libsimt_b200.so).  See DESIGN.md.
 """
-from .head import HeadRunner, SimTHead, check_errors, simt_head
+from .head import HeadRunner, HostPrefetcher, SimTHead, check_errors, simt_head
 from .hist import ConfusionMeter, build_lut, fast_hist, label_mapping, per_class_iu
 from .loss import CrossEntropy2d, EntropyLoss
 from .ntm import sig_NTM, sig_W
@@ -11,7 +11,7 @@ from .regularizers import (anchor_loss, anchor_stats, bilinear_gather, convex_lo
                            w_fit_loss)
 
 __all__ = [
-    "simt_head", "SimTHead", "HeadRunner", "check_errors", "CrossEntropy2d", "EntropyLoss", "sig_NTM", "sig_W",
+    "simt_head", "SimTHead", "HeadRunner", "HostPrefetcher", "check_errors", "CrossEntropy2d", "EntropyLoss", "sig_NTM", "sig_W",
     "fast_hist", "per_class_iu", "label_mapping", "ConfusionMeter", "build_lut",
     "convex_loss", "volume_loss", "anchor_loss", "w_fit_loss", "t_regularizers", "anchor_stats", "bilinear_gather",
 ]

@@ -249,3 +249,44 @@ class HeadRunner:
     def global_loss(self):
         """loss over the all-reduced stats (sharded runs); a 0-dim f64 tensor, no sync."""
         return self.stats[0] / self.stats[1]
+
+
+class HostPrefetcher:
+    """Double-buffered pinned-host -> device uploader for (logits, labels) batches.
+
+    ``submit(logits_host, labels_host)`` enqueues the copies of the NEXT batch on a side stream;
+    ``get()`` makes the compute stream wait for them and returns the device tensors.  While a step
+    computes, the next step's 9 MB of inputs cross PCIe -- the usual input pipeline of a training loop.
+    """
+
+    def __init__(self, B, CK, h, w, H, W, device=None, label_dtype=torch.uint8):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.bufs = [(torch.empty(B, CK, h, w, dtype=torch.float32, device=self.dev),
+                      torch.empty(B, H, W, dtype=label_dtype, device=self.dev)) for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.slot = 0
+        self.pending = None
+
+    def submit(self, logits_host: torch.Tensor, labels_host: torch.Tensor) -> None:
+        slot = self.slot
+        lg, lab = self.bufs[slot]
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[slot])          # the compute that last used this slot is done
+            lg.copy_(logits_host, non_blocking=True)
+            lab.copy_(labels_host, non_blocking=True)
+            self.events[slot].record(self.stream)
+        self.pending = slot
+        self.slot ^= 1
+
+    def get(self):
+        slot = self.pending
+        torch.cuda.current_stream(self.dev).wait_event(self.events[slot])
+        return self.bufs[slot]
+
+    def release(self, slot_tensors) -> None:
+        """Call after the step that consumed ``slot_tensors`` has been enqueued."""
+        for i, b in enumerate(self.bufs):
+            if b[0] is slot_tensors[0]:
+                self.free[i].record(torch.cuda.current_stream(self.dev))
