@@ -521,23 +521,29 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // A pair that straddles a label boundary is split (pixel 1 waits for the next step), so a step never
           // mixes two T columns; the column switch itself is per lane and shuffle-free.  The loop is
           // WARP-UNIFORM (vote on "anyone left"), lanes that are done run predicated-off steps.
+          // Rows alternate direction (boustrophedon): a run that contains a label boundary A|B is walked
+          // A..B on one row and B..A on the next, so the lane switches its label column (and flushes its dT
+          // accumulators) once per row instead of twice.
+          const bool reverse = ((Y - Yall0) & 1) != 0;
           auto run_row = [&](auto check_underflow) {
-            int pos = 0;
-            while (__any_sync(0xffffffffu, pos < nrun)) {
+            int done = 0;  // pixels of this lane's run already consumed
+            while (__any_sync(0xffffffffu, done < nrun)) {
+              // the next two pixels in walking order: p0, then p1 = p0 +- 1
+              const int p0 = reverse ? nrun - 1 - done : done;
+              const int p1 = reverse ? p0 - 1 : p0 + 1;
+              const bool in0 = done < nrun, in1 = done + 1 < nrun;
               unsigned c0, c1;
-              if (pos < 7) {
-                const unsigned two = (unsigned)(codes >> (8 * pos));
-                c0 = two & 0xffu;
-                c1 = (two >> 8) & 0xffu;
+              if (nrun <= 8) {
+                c0 = in0 ? (unsigned)(codes >> (8 * p0)) & 0xffu : 0xffu;
+                c1 = in1 ? (unsigned)(codes >> (8 * p1)) & 0xffu : 0xffu;
               } else {  // runs longer than the 8 prefetched labels (large up-sampling factors)
-                c0 = (pos < nrun) ? ((pos < 8) ? (unsigned)(codes >> 56) & 0xffu
-                                                : LabelFetch<LabelT>::one(labels, rowbase + pos, A.ignore, C)) : 0xffu;
-                c1 = (pos + 1 < nrun) ? LabelFetch<LabelT>::one(labels, rowbase + pos + 1, A.ignore, C) : 0xffu;
+                c0 = in0 ? LabelFetch<LabelT>::one(labels, rowbase + p0, A.ignore, C) : 0xffu;
+                c1 = in1 ? LabelFetch<LabelT>::one(labels, rowbase + p1, A.ignore, C) : 0xffu;
               }
               bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
               bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
               if (!(v0 && v1)) {  // neither a class nor the ignore label (nor padding past the run)?
-                if ((!v0 && (int)c0 != ign8 && pos < nrun) || (!v1 && (int)c1 != ign8 && pos + 1 < nrun)) bad_label = true;
+                if ((!v0 && (int)c0 != ign8 && in0) || (!v1 && (int)c1 != ign8 && in1)) bad_label = true;
               }
               int adv = 2;
               if (v0 && v1 && c0 != c1) { v1 = false; adv = 1; }  // label boundary inside the pair
@@ -546,8 +552,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 if (BWD && cur >= 0) flush_lane();
                 switch_column(lab);
               }
-              body(check_underflow, lambda_of(xa + pos, A.sx, cx), lambda_of(xa + pos + 1, A.sx, cx), v0, v1);
-              pos += adv;
+              body(check_underflow, lambda_of(xa + p0, A.sx, cx), lambda_of(xa + p1, A.sx, cx), v0, v1);
+              done += adv;
             }
           };
           if (__all_sync(0xffffffffu, range_safe)) run_row(std::false_type{});
@@ -649,26 +655,37 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   }
 }
 
-// Fixed-order reduction of the per-CTA partials.  blockDim = (32 outputs, 8 slices of the CTA range):
-// consecutive threads read consecutive tile entries (coalesced), every slice sums its CTAs in order and
-// the 8 slice sums are added in order.  The tiles are re-zeroed for the next call on the way.  The last
-// block reduces loss / count and re-arms the unit scheduler.
-__global__ void __launch_bounds__(256) head_finalize_kernel(
+// Fixed-order reduction of the per-CTA partials.  blockDim = (32 outputs, 32 slices of the CTA range):
+// consecutive threads read consecutive tile entries (coalesced); every slice first issues ALL its loads
+// (independent, many in flight), sums them in order, then re-zeroes the entries for the next call; the
+// 32 slice sums are added in order.  The last block reduces loss / count and re-arms the unit scheduler.
+static constexpr int kFinSlices = 32;
+static constexpr int kFinMaxPer = 40;  // partials per slice held in registers: grid <= 32 * 40 = 1280 CTAs
+
+__global__ void __launch_bounds__(1024) head_finalize_kernel(
     float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
     int nparts, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
     double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err) {
   const int ndt = C * CKP;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  __shared__ double sm[8][33];
-  __shared__ long long smi[8];
+  __shared__ double sm[kFinSlices][33];
+  __shared__ long long smi[kFinSlices];
   if ((int)blockIdx.x < (int)gridDim.x - 1) {
     const int o = blockIdx.x * 32 + tx;  // output index in the [y][k] layout of the tiles
     double s = 0.0;
     if (o < ndt && mode != MODE_FWD) {
-      for (int g = ty; g < nparts; g += 8) {
-        float* p = part_dT + (size_t)g * ndt + o;
-        s += (double)*p;
-        *p = 0.f;
+      float v[kFinMaxPer];
+#pragma unroll
+      for (int q = 0; q < kFinMaxPer; ++q) {
+        const int g = ty + q * kFinSlices;
+        v[q] = (g < nparts) ? part_dT[(size_t)g * ndt + o] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < kFinMaxPer; ++q) s += (double)v[q];
+#pragma unroll
+      for (int q = 0; q < kFinMaxPer; ++q) {
+        const int g = ty + q * kFinSlices;
+        if (g < nparts) part_dT[(size_t)g * ndt + o] = 0.f;
       }
     }
     sm[ty][tx] = s;
@@ -676,7 +693,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(
     if (ty == 0 && o < ndt) {
       double t = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t += sm[q][tx];
+      for (int q = 0; q < kFinSlices; ++q) t += sm[q][tx];
       const int y = o / CKP, k = o - y * CKP;
       if (k < CK) {
         if (stats) stats[2 + k * C + y] = -t;
@@ -686,7 +703,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(
   } else {
     double l = 0.0;
     long long c = 0;
-    for (int g = threadIdx.x; g < nparts; g += 256) { l += part_loss[g]; c += part_cnt[g]; }
+    for (int g = threadIdx.x; g < nparts; g += blockDim.x) { l += part_loss[g]; c += part_cnt[g]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       l += __shfl_xor_sync(0xffffffffu, l, o);
@@ -696,7 +713,7 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       l = 0.0; c = 0;
-      for (int q = 0; q < 8; ++q) { l += sm[q][0]; c += smi[q]; }
+      for (int q = 0; q < kFinSlices; ++q) { l += sm[q][0]; c += smi[q]; }
       *counter = 0ULL;  // the main kernel of this call has finished: re-arm the unit scheduler
       const double ls = -kLn2 * l;
       if (stats) { stats[0] = ls; stats[1] = (double)c; }
@@ -730,7 +747,7 @@ __global__ void head_scale_kernel(float* __restrict__ dlogits, long long n, cons
 // host side
 // ------------------------------------------------------------------------------------------
 // workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f32 x G*C*CKPmax]
-static constexpr int kMaxGridPerSm = 8;
+static constexpr int kMaxGridPerSm = 8;   // grid <= 148 * 8 = 1184 <= kFinSlices * kFinMaxPer
 static constexpr int kMaxCKP = 64;
 
 struct Tuning { int ur, unused, threads, lpr; };
@@ -910,7 +927,7 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   rc = dispatch_all(mode, label_bytes, A, P, st, &grid);
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
-  head_finalize_kernel<<<fgrid, 256, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, mode, gscale,
+  head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, mode, gscale,
                                               A.counter, stats, loss_mean, dT_out, err_flag);
   return (int)cudaGetLastError();
 }
