@@ -1,0 +1,75 @@
+"""GPU, 2 ranks over NCCL (skipped on a 1-GPU box): the batch-sharded fused head equals the
+single-GPU answer on the global batch (BASELINE config 5 semantics, small shape)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import datetime
+    import torch.distributed as dist
+    import simt_b200
+    from simt_b200 import dist as sd
+    from oracle import simt_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                            timeout=datetime.timedelta(seconds=60))
+    try:
+        logits, labels = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=3, coherent=True, block=(12, 20))
+        torch.manual_seed(7)
+        T = simt_b200.sig_NTM(19, 4)().detach()
+        lg = sd.shard_batch(logits, rank, world).to(dev).requires_grad_(True)
+        lb = sd.shard_batch(labels, rank, world).to(dev)
+        Tt = T.to(dev).requires_grad_(True)
+        loss = simt_b200.simt_head(lg, Tt, lb, (64, 128), group=dist.group.WORLD)
+        loss.backward()
+        gt, pr = O.synth_eval_pair(128, 256, seed=rank, block=(24, 40))
+        meter = simt_b200.ConfusionMeter(19, mapping=O.CITYSCAPES_LABEL2TRAIN, device=dev)
+        meter.update(gt, pr)
+        sd.reduce_hist(meter.hist)
+        torch.save({"loss": loss.detach().cpu(), "dl": lg.grad.cpu(), "dT": Tt.grad.cpu(), "hist": meter.hist.cpu()},
+                   os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_head_equals_global_batch(tmp_path):
+    import torch.multiprocessing as mp
+    import simt_b200
+    from simt_b200 import dist as sd
+    from oracle import simt_oracle as O
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    logits, labels = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=3, coherent=True, block=(12, 20))
+    torch.manual_seed(7)
+    T = simt_b200.sig_NTM(19, 4)().detach()
+    lo, dlo, dTo = O.simt_head_fwd_bwd(logits, T, labels, (64, 128), torch.float64)
+    for r in range(world):
+        assert abs(float(res[r]["loss"]) - float(lo)) <= 1e-5 * abs(float(lo))
+        assert float((res[r]["dT"].double() - dTo).norm() / dTo.norm()) <= 1e-5     # dT summed over ranks
+        a, b = sd.shard_range(6, r, world)
+        ref = dlo[a:b]
+        assert float((res[r]["dl"].double() - ref).norm() / ref.norm()) <= 1e-5      # dLogits stay local
+    hist = np.zeros((19, 19), dtype=np.int64)
+    for r in range(world):
+        gt, pr = O.synth_eval_pair(128, 256, seed=r, block=(24, 40))
+        hist += O.fast_hist(O.label_mapping(gt, np.array(O.CITYSCAPES_LABEL2TRAIN)).flatten(), pr.flatten(), 19)
+    assert np.array_equal(res[0]["hist"].numpy(), hist) and np.array_equal(res[1]["hist"].numpy(), hist)
