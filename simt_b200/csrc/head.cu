@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   int cur = -1;
   double loss_d = 0.0;  // sum of log2 q over this thread's valid pixels
   long long cnt = 0;
-  bool bad_label = false;
+  int badf = 0;  // contract violation seen (a label that is neither a class nor the ignore label)
 
   auto claim = [&]() -> long long {
     unsigned long long u = 0;
@@ -372,24 +372,28 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
       {
         const float* src = A.logits + ((size_t)b * CK + kbase) * h * w;
         __syncwarp();
+        // all 4*CPL corner loads are issued before the first one is used (one exposed L2 latency, not ten)
+        float c00[CPL], c01[CPL], c10[CPL], c11[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const float pad = cell_ok ? kPadLogit : 0.f;
+          c00[j] = c01[j] = c10[j] = c11[j] = pad;
+          if (cell_ok && kbase + j < CK) {
+            const float* p = src + (size_t)j * h * w;
+            c00[j] = __ldg(p + gy0 * w + gx0); c01[j] = __ldg(p + gy0 * w + gx1);
+            c10[j] = __ldg(p + gy1 * w + gx0); c11[j] = __ldg(p + gy1 * w + gx1);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-          float c00[2], c01[2], c10[2], c11[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int j = 2 * q + t;
-            c00[t] = c01[t] = kPadLogit; c10[t] = c11[t] = kPadLogit;
-            if (!cell_ok) { c00[t] = c01[t] = c10[t] = c11[t] = 0.f; }
-            else if (kbase + j < CK) {
-              const float* p = src + (size_t)j * h * w;
-              c00[t] = __ldg(p + gy0 * w + gx0) * kLog2e; c01[t] = __ldg(p + gy0 * w + gx1) * kLog2e;
-              c10[t] = __ldg(p + gy1 * w + gx0) * kLog2e; c11[t] = __ldg(p + gy1 * w + gx1) * kLog2e;
-            }
-          }
-          Lw[(0 * NP + q) * 32] = make_float2(c00[0], c00[1]);
-          Lw[(1 * NP + q) * 32] = make_float2(c10[0] - c00[0], c10[1] - c00[1]);
-          Lw[(2 * NP + q) * 32] = make_float2(c01[0], c01[1]);
-          Lw[(3 * NP + q) * 32] = make_float2(c11[0] - c01[0], c11[1] - c01[1]);
+          const bool r0 = cell_ok && kbase + 2 * q < CK, r1 = cell_ok && kbase + 2 * q + 1 < CK;  // real channels
+          const float s0 = r0 ? kLog2e : 1.f, s1 = r1 ? kLog2e : 1.f;   // padding stays at kPadLogit / 0
+          const float a0 = c00[2 * q] * s0, a1 = c00[2 * q + 1] * s1;
+          const float b0 = c01[2 * q] * s0, b1 = c01[2 * q + 1] * s1;
+          Lw[(0 * NP + q) * 32] = make_float2(a0, a1);
+          Lw[(1 * NP + q) * 32] = make_float2(c10[2 * q] * s0 - a0, c10[2 * q + 1] * s1 - a1);
+          Lw[(2 * NP + q) * 32] = make_float2(b0, b1);
+          Lw[(3 * NP + q) * 32] = make_float2(c11[2 * q] * s0 - b0, c11[2 * q + 1] * s1 - b1);
         }
         __syncwarp();
       }
@@ -540,15 +544,16 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 c0 = in0 ? LabelFetch<LabelT>::one(labels, rowbase + p0, A.ignore, C) : 0xffu;
                 c1 = in1 ? LabelFetch<LabelT>::one(labels, rowbase + p1, A.ignore, C) : 0xffu;
               }
-              bool v0 = c0 < (unsigned)C && (int)c0 != ign8;
-              bool v1 = c1 < (unsigned)C && (int)c1 != ign8;
-              if (!(v0 && v1)) {  // neither a class nor the ignore label (nor padding past the run)?
-                if ((!v0 && (int)c0 != ign8 && in0) || (!v1 && (int)c1 != ign8 && in1)) bad_label = true;
-              }
-              int adv = 2;
-              if (v0 && v1 && c0 != c1) { v1 = false; adv = 1; }  // label boundary inside the pair
+              // branch-free validity / contract / pair-split logic (bitwise on purpose: no short-circuit branches)
+              const bool k0 = c0 < (unsigned)C, k1 = c1 < (unsigned)C;        // is a class id
+              const bool g0 = (int)c0 != ign8, g1 = (int)c1 != ign8;          // is not the ignore label
+              badf |= (int)((!k0 & g0 & in0) | (!k1 & g1 & in1));             // neither class nor ignore (nor padding)
+              const bool v0 = k0 & g0;
+              const bool split = v0 & k1 & g1 & (c0 != c1);                    // label boundary inside the pair
+              const bool v1 = k1 & g1 & !split;
+              const int adv = split ? 1 : 2;
               const int lab = v0 ? (int)c0 : (int)c1;
-              if ((v0 || v1) && lab != cur) {
+              if ((v0 | v1) & (lab != cur)) {   // the only branch: a column switch (rare on coherent maps)
                 if (BWD && cur >= 0) flush_lane();
                 switch_column(lab);
               }
@@ -638,7 +643,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 
   // ---- CTA epilogue: partials ---------------------------------------------------------------
   if (BWD && cur >= 0) flush_lane();
-  if (bad_label) atomicOr(A.err, SIMT_ERRBIT_LABEL_RANGE);
+  if (badf) atomicOr(A.err, SIMT_ERRBIT_LABEL_RANGE);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
