@@ -803,6 +803,7 @@ static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* gr
 #endif
 #define SIMT_HEAD_CONFIGS(X) \
   X(10, 2, 128, SIMT_MINB_FWD, SIMT_MINB_BWD)        \
+  X(12, 2, 128, 3, 2)                                \
   X(6, 4, 128, 4, 4)         \
   X(10, 4, 128, 4, 3)        \
   X(16, 4, 128, 3, 2)
