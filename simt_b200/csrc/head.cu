@@ -294,11 +294,10 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   long long cnt = 0;
   int badf = 0;  // contract violation seen (a label that is neither a class nor the ignore label)
 
-  auto claim = [&]() -> long long {
-    unsigned long long u = 0;
-    if (lane == 0) u = atomicAdd(A.counter, 1ULL);
-    return (long long)__shfl_sync(0xffffffffu, u, 0);
-  };
+  // lane 0 claims; the value is only broadcast when the claimed unit is started, so the atomic's
+  // round trip to L2 overlaps the unit in progress
+  auto claim_raw = [&]() -> unsigned long long { return (lane == 0) ? atomicAdd(A.counter, 1ULL) : 0ULL; };
+  auto claim_get = [&](unsigned long long raw) -> long long { return (long long)__shfl_sync(0xffffffffu, raw, 0); };
   auto switch_column = [&](int y) {
     cur = y;
     const float2* src = reinterpret_cast<const float2*>(Ts + y * CKP + kbase);
@@ -317,9 +316,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     for (int q = 0; q < NP; ++q) D2[q] = make_float2(0.f, 0.f);
   };
 
-  long long unit = claim();
+  long long unit = claim_get(claim_raw());
+  unsigned long long next_raw = claim_raw();
   while (unit < A.nunits) {
-    const long long next_unit = claim();  // in flight while this unit is processed
     const int per_img = A.units_y * A.units_x;
     const int b = (int)(unit / per_img);
     const int urem = (int)(unit - (long long)b * per_img);
@@ -335,23 +334,6 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     const int gx0 = min(cx, w - 1), gx1 = min(cx + 1, w - 1);
     const int edge_gx = min(ux * CPW + ncell_u, w - 1);          // node column right of the unit
     float loss_acc = 0.f;
-    if (next_unit < A.nunits) {
-      // pull the next unit's corner logits (and its first label row) towards L2 while this unit computes
-      const int nb = (int)(next_unit / per_img);
-      const int nrem = (int)(next_unit - (long long)nb * per_img);
-      const int nuy = (nrem / A.units_x) / A.rs, nux = nrem - (nrem / A.units_x) * A.units_x;
-      const int ncx = min(nux * CPW + pidx, A.ncx - 1), ncy0 = nuy * A.ur;
-      const float* np0 = A.logits + (((size_t)nb * CK + kbase) * h + min(ncy0, h - 1)) * w + min(ncx, w - 1);
-#pragma unroll
-      for (int j = 0; j < CPL; j += 2)   // one 128-byte line usually covers a node pair and its neighbours
-        if (kbase + j < CK) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(np0 + (size_t)j * h * w));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(np0 + (size_t)j * h * w + w));
-        }
-      if (sub == 0)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + ((long long)nb * A.H + ys_tab[ncy0]) * A.W + xs_tab[ncx]));
-    }
-
     const int cy_begin = uy * A.ur, cy_end = min(A.ncy, (uy + 1) * A.ur);
     // this unit's pixel rows: all rows of its cell-rows, or the part-th slice of the single cell-row
     const int Yall0 = ys_tab[cy_begin], Yall1 = ys_tab[cy_end];
@@ -638,7 +620,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     }  // cell-rows of the unit
 
     loss_d += (double)loss_acc;
-    unit = next_unit;
+    unit = claim_get(next_raw);
+    next_raw = claim_raw();
   }
 
   // ---- CTA epilogue: partials ---------------------------------------------------------------
