@@ -423,8 +423,13 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // channel pairs packed into fp32x2 instructions).  WARP-UNIFORM: lane groups exchange partial
           // sums with full-mask shuffles, so invalid lanes/pixels are predicated off (w0/w1), never
           // branched around.
-          // both pixels of a step belong to the lane's current label column `cur`
-          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1) {
+          // pixel 0 belongs to the lane's current label column `cur`; pixel 1 too unless `c1x >= 0`, in which
+          // case the pair straddles a label boundary and pixel 1 uses column c1x (its T column is read from
+          // shared memory where needed -- predicated loads, no extra live registers, no split step)
+          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1,
+                          const int c1x) {
+            const bool strad = c1x >= 0;
+            const float2* T1 = reinterpret_cast<const float2*>(Ts + (strad ? c1x : 0) * CKP + kbase);
             const float2 L0 = bcast2(lam0), L1 = bcast2(lam1);
             float2 e0[NP], e1[NP];
             float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0, ns0 = sum0, ns1 = sum0;
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               sum0 = fadd2(sum0, e0[q]);
               sum1 = fadd2(sum1, e1[q]);
               ns0 = ffma2(e0[q], nTc[q], ns0);
-              ns1 = ffma2(e1[q], nTc[q], ns1);
+              ns1 = ffma2(e1[q], strad ? T1[q] : nTc[q], ns1);
             }
             float su0 = group_sum<LPR>(sum0.x + sum0.y, 0xffffffffu);
             float su1 = group_sum<LPR>(sum1.x + sum1.y, 0xffffffffu);
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 su0 += e0[q].x + e0[q].y;
                 su1 += e1[q].x + e1[q].y;
                 s0 -= e0[q].x * nTc[q].x + e0[q].y * nTc[q].y;
-                s1 -= e1[q].x * nTc[q].x + e1[q].y * nTc[q].y;
+                const float2 tq1 = strad ? T1[q] : nTc[q];
+                s1 -= e1[q].x * tq1.x + e1[q].y * tq1.y;
               }
               su0 = group_sum<LPR>(su0, 0xffffffffu);
               su1 = group_sum<LPR>(su1, 0xffffffffu);
@@ -491,22 +497,27 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #pragma unroll
               for (int q = 0; q < NP; ++q) {
                 // c = (p_k - p_k T_ky / q) / e_k = rs - T_ky * is ;  c1 = lambda * c
-                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(nTc[q], I1, R1);
-                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(nTc[q], LI1, LR1);
+                const float2 tq1 = strad ? T1[q] : nTc[q];
+                const float2 ca = ffma2(nTc[q], I0, R0), cb = ffma2(tq1, I1, R1);
+                const float2 c1a = ffma2(nTc[q], LI0, LR0), c1b = ffma2(tq1, LI1, LR1);
                 Gs[q] = ffma2(e0[q], ca, Gs[q]);
                 Gs[q] = ffma2(e1[q], cb, Gs[q]);
                 G1[q] = ffma2(e0[q], c1a, G1[q]);
                 G1[q] = ffma2(e1[q], c1b, G1[q]);
-                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q
-                D2[q] = ffma2(e1[q], I1, D2[q]);
+                D2[q] = ffma2(e0[q], I0, D2[q]);   // p_k / q, column `cur`
               }
+              if (strad) {  // pixel 1 opens a new label column
+                if (cur >= 0) flush_lane();
+                switch_column(c1x);
+              }
+#pragma unroll
+              for (int q = 0; q < NP; ++q) D2[q] = ffma2(e1[q], I1, D2[q]);
             }
           };
 
-          // ---- the pixel loop: every lane walks its own run with a cursor `pos`, two pixels per step.
-          // A pair that straddles a label boundary is split (pixel 1 waits for the next step), so a step never
-          // mixes two T columns; the column switch itself is per lane and shuffle-free.  The loop is
-          // WARP-UNIFORM (vote on "anyone left"), lanes that are done run predicated-off steps.
+          // ---- the pixel loop: two pixels of every lane's run per step; the column switch is per lane and
+          // shuffle-free.  The loop is WARP-UNIFORM (vote on "anyone left"), lanes that are done run
+          // predicated-off steps.
           // Rows alternate direction (boustrophedon): a run that contains a label boundary A|B is walked
           // A..B on one row and B..A on the next, so the lane switches its label column (and flushes its dT
           // accumulators) once per row instead of twice.
@@ -530,17 +541,15 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
               const bool k0 = c0 < (unsigned)C, k1 = c1 < (unsigned)C;        // is a class id
               const bool g0 = (int)c0 != ign8, g1 = (int)c1 != ign8;          // is not the ignore label
               badf |= (int)((!k0 & g0 & in0) | (!k1 & g1 & in1));             // neither class nor ignore (nor padding)
-              const bool v0 = k0 & g0;
-              const bool split = v0 & k1 & g1 & (c0 != c1);                    // label boundary inside the pair
-              const bool v1 = k1 & g1 & !split;
-              const int adv = split ? 1 : 2;
+              const bool v0 = k0 & g0, v1 = k1 & g1;
               const int lab = v0 ? (int)c0 : (int)c1;
-              if ((v0 | v1) & (lab != cur)) {   // the only branch: a column switch (rare on coherent maps)
+              if ((v0 | v1) & (lab != cur)) {   // a column switch before the pair (rare on coherent maps)
                 if (BWD && cur >= 0) flush_lane();
                 switch_column(lab);
               }
-              body(check_underflow, lambda_of(xa + p0, A.sx, cx), lambda_of(xa + p1, A.sx, cx), v0, v1);
-              done += adv;
+              const int c1x = (v0 & v1 & (c0 != c1)) ? (int)c1 : -1;   // label boundary inside the pair
+              body(check_underflow, lambda_of(xa + p0, A.sx, cx), lambda_of(xa + p1, A.sx, cx), v0, v1, c1x);
+              done += 2;
             }
           };
           if (__all_sync(0xffffffffu, range_safe)) run_row(std::false_type{});
