@@ -89,8 +89,8 @@ def main():
         return
     # ---- histograms: BIG launches (32 images = 64 Mi pixels per launch), 3 rotating sets > L2 ----------
     lut = torch.from_numpy(simt_b200.build_lut(O.CITYSCAPES_LABEL2TRAIN)).to(dev)
-    nimg, nsets = 32, 3
-    for coherent in ('clean', 'noisy', False):
+    nimg, nsets = (256, 2) if 'bighist' in sys.argv else (32, 3)
+    for coherent in (('clean',) if 'bighist' in sys.argv else ('clean', 'noisy', False)):
         gt_sets, pr_sets = [], []
         for s_ in range(nsets):
             gts, prs = [], []
@@ -102,8 +102,8 @@ def main():
             pr_sets.append(torch.stack(prs).repeat(nimg // 8, 1, 1).to(dev).reshape(-1))
         npx = gt_sets[0].numel()
         for (rows, cols, use_lut) in ((19, 19, True), (34, 19, False), (19, 1, False)):
-            for mode in (0,):
-                for warps, unroll in ((16, 2), (16, 4), (16, 1), (8, 4), (8, 2), (32, 2)):
+            for mode in (0, 9):
+                for warps, unroll in ((16, 1), (16, 2), (16, 4), (8, 4)):
                     lib.simt_hist_set_tuning(mode, warps, unroll)
                     hist = torch.zeros(rows * cols, dtype=torch.int64, device=dev)
                     try:

@@ -34,6 +34,7 @@ struct HistArgs {
   long long n;           // pixels
   const uint8_t* lut;    // null = identity
   int n_rows, n_cols, nbins;
+  int probe;             // benchmark probe: only stream the inputs (load-path ceiling), counts are garbage
   unsigned long long* hist;
   int* err;
 };
@@ -44,6 +45,7 @@ struct Accum {
   unsigned* my_hist;  // this lane's copy of the CTA histogram ([nbins] u32, shared atomics)
   const uint8_t* lut_s;
   int n_rows, n_cols, nbins;
+  int probe;             // benchmark probe: only stream the inputs (load-path ceiling), counts are garbage
   bool bad;
 
   __device__ __forceinline__ int bin_of(unsigned araw, unsigned b) {
@@ -75,7 +77,10 @@ __global__ void __launch_bounds__(512) hist_u8_kernel(const HistArgs A) {
   acc.my_hist = cta_hist + (lane % kRep) * hstride; acc.lut_s = lut_s;
   acc.n_rows = A.n_rows; acc.n_cols = A.n_cols; acc.nbins = A.nbins; acc.bad = false;
 
-  const long long ngroups = A.n >> 4;  // 16-pixel groups (pointers are 16-byte aligned)
+  // a lane-iteration is one 128-bit load of a and one of b (16 pixels), or -- single-array class histogram --
+  // two consecutive 128-bit loads of a (32 pixels), so both cases move 32 B per lane per iteration
+  constexpr int GPX = HAS_B ? 16 : 32;
+  const long long ngroups = A.n / GPX;  // (pointers are 16-byte aligned)
   const uint4* a4 = reinterpret_cast<const uint4*>(A.a);
   const uint4* b4 = reinterpret_cast<const uint4*>(A.b);
   const long long gwarp = (long long)blockIdx.x * nwarps + warp;
@@ -95,30 +100,35 @@ __global__ void __launch_bounds__(512) hist_u8_kernel(const HistArgs A) {
       const long long g = c * chunk + (long long)u * 32 + lane;
       ok[u] = g < ngroups;
       if (ok[u]) {
-        va[u] = ldg_stream_u4(a4 + g);
-        if (HAS_B) vb[u] = ldg_stream_u4(b4 + g);
+        va[u] = ldg_stream_u4(HAS_B ? a4 + g : a4 + 2 * g);
+        vb[u] = ldg_stream_u4(HAS_B ? b4 + g : a4 + 2 * g + 1);
       }
+    }
+    if (A.probe) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (ok[u]) run_cnt ^= va[u].x ^ va[u].y ^ va[u].z ^ va[u].w ^ vb[u].x ^ vb[u].y ^ vb[u].z ^ vb[u].w;
+      continue;
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       if (!ok[u]) continue;
       const unsigned aw[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-      unsigned bw[4] = {0, 0, 0, 0};
-      if (HAS_B) { bw[0] = vb[u].x; bw[1] = vb[u].y; bw[2] = vb[u].z; bw[3] = vb[u].w; }
-      const unsigned a0 = aw[0] & 0xffu, b0 = bw[0] & 0xffu;
-      const unsigned ar = a0 * 0x01010101u, br = b0 * 0x01010101u;
+      const unsigned bw[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};   // b pixels, or the next 16 a pixels
+      const unsigned a0 = aw[0] & 0xffu, b0 = HAS_B ? (bw[0] & 0xffu) : 0u;
+      const unsigned ar = a0 * 0x01010101u, br = HAS_B ? b0 * 0x01010101u : ar;
       // one LOP3 per word pair: (x ^ r) | (y ^ r)
       const unsigned da = ((aw[0] ^ ar) | (aw[1] ^ ar)) | ((aw[2] ^ ar) | (aw[3] ^ ar));
-      const unsigned db = HAS_B ? (((bw[0] ^ br) | (bw[1] ^ br)) | ((bw[2] ^ br) | (bw[3] ^ br))) : 0u;
+      const unsigned db = ((bw[0] ^ br) | (bw[1] ^ br)) | ((bw[2] ^ br) | (bw[3] ^ br));
       if ((da | db) == 0u) {
         const int idx = acc.bin_of(a0, b0);
         if (idx == run_bin) {
-          run_cnt += 16;
+          run_cnt += GPX;
         } else {
           acc.add(run_bin, run_cnt);  // finished run (rare)
-          run_bin = idx; run_cnt = 16;
+          run_bin = idx; run_cnt = GPX;
         }
-      } else {
+      } else if (HAS_B) {
 #pragma unroll
         for (int wd = 0; wd < 4; ++wd) {
           const unsigned x = aw[wd], y = bw[wd];
@@ -130,14 +140,26 @@ __global__ void __launch_bounds__(512) hist_u8_kernel(const HistArgs A) {
             for (int q = 0; q < 4; ++q) acc.add(acc.bin_of((x >> (8 * q)) & 0xffu, (y >> (8 * q)) & 0xffu), 1u);
           }
         }
+      } else {
+#pragma unroll
+        for (int wd = 0; wd < 8; ++wd) {
+          const unsigned x = wd < 4 ? aw[wd & 3] : bw[wd & 3];
+          const unsigned xa = x & 0xffu;
+          if (x == xa * 0x01010101u) {
+            acc.add(acc.bin_of(xa, 0u), 4u);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc.add(acc.bin_of((x >> (8 * q)) & 0xffu, 0u), 1u);
+          }
+        }
       }
     }
   }
   acc.add(run_bin, run_cnt);
 
-  // tail pixels (n % 16) by one thread of CTA 0
+  // tail pixels (n % GPX) by one thread of CTA 0
   if (blockIdx.x == 0 && tid == 0) {
-    for (long long i = ngroups << 4; i < A.n; ++i) acc.add(acc.bin_of(A.a[i], HAS_B ? A.b[i] : 0u), 1u);
+    for (long long i = ngroups * GPX; i < A.n; ++i) acc.add(acc.bin_of(A.a[i], HAS_B ? A.b[i] : 0u), 1u);
   }
   if (acc.bad) atomicOr(A.err, SIMT_ERRBIT_PRED_RANGE);
   __syncthreads();
@@ -236,14 +258,15 @@ static int run_hist(const void* a, int a_bytes, const void* b, int b_bytes, long
       A.a = static_cast<const uint8_t*>(a) + off;
       A.b = b ? static_cast<const uint8_t*>(b) + off : nullptr;
       A.n = len; A.lut = lut; A.n_rows = n_rows; A.n_cols = n_cols; A.nbins = (int)nbins;
-      A.hist = h; A.err = err_flag;
-      int unroll = g_hist_tuning.unroll > 0 ? g_hist_tuning.unroll : 1;
+      A.hist = h; A.err = err_flag; A.probe = (g_hist_tuning.mode == 9);
+      // more loads in flight per lane pay off once the launch is long enough to reach steady state
+      int unroll = g_hist_tuning.unroll > 0 ? g_hist_tuning.unroll : (len >= (1LL << 29) ? 4 : 1);
       int warps = g_hist_tuning.warps > 0 ? g_hist_tuning.warps : 16;
       if (warps > 16) warps = 16;
       const size_t smem = 256 + (size_t)kRep * ((size_t)A.nbins | 1) * 4;   // <= 33 KB for 1024 bins
       int ctas_per_sm = 2048 / (warps * 32);
       if (ctas_per_sm < 1) ctas_per_sm = 1;
-      const long long ngroups = len >> 4;
+      const long long ngroups = len / (b ? 16 : 32);
       long long need = (ngroups + 32LL * unroll * warps - 1) / (32LL * unroll * warps);
       long long grid = (long long)di.sm_count * ctas_per_sm;
       if (grid > need) grid = need;
