@@ -205,3 +205,47 @@ def test_reference_training_lines_with_fused_head():
     assert abs(float(out) - float(ref)) <= TOL * abs(float(ref))
     _check(lg2.grad.cpu().numpy(), g_ref.cpu().numpy(), "dlogits vs torch-CUDA eager")
     _check(ntm.NTM.grad.cpu().numpy(), n_ref.cpu().numpy(), "dNTM vs torch-CUDA eager")
+
+
+@pytest.mark.parametrize("B,K", [(64, 0), (16, 15)])
+def test_full_size_invariants(B, K):
+    """BASELINE config 5 / 3 sizes (too big for the CPU oracle in a test): size-independent properties.
+
+    * softmax gradient: sum_k dz_k = (1/N)(sum_k p_k - sum_k p_k T_ky / q) = 0 at every pixel, and U^T is
+      linear, so dLogits summed over channels vanishes at every low-res node;
+    * <T, dT> = -(1/N) sum_pixels sum_k p_k T_ky / q = -1;
+    * permuting the batch permutes dLogits and leaves loss and dT unchanged (to rounding);
+    * doubling every image (batch concatenated with itself) leaves loss and dT unchanged and halves dLogits.
+    """
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    CK = 19 + K
+    logits, labels = O.synth_head_inputs(B, CK, 65, 129, 512, 1024, seed=99, coherent=True, block=(36, 52),
+                                         class_dist=class_dist())
+    torch.manual_seed(5)
+    T = simt_b200.sig_NTM(19, K)().detach().to(dev)
+
+    def run(lg_cpu, lab_cpu):
+        lg = lg_cpu.to(dev).requires_grad_(True)
+        Tt = T.clone().requires_grad_(True)
+        loss = simt_b200.simt_head(lg, Tt, lab_cpu.to(dev), (512, 1024))
+        loss.backward()
+        return loss.detach(), lg.grad, Tt.grad
+
+    loss, dl, dT = run(logits, labels)
+    assert torch.isfinite(loss) and 0.0 < float(loss) < 20.0
+    node_sum = dl.sum(dim=1)
+    assert float(node_sum.abs().max()) <= 1e-5 * float(dl.abs().max())
+    assert abs(float((T * dT).sum()) + 1.0) <= 1e-5
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    loss_p, dl_p, dT_p = run(logits[perm], labels[perm])
+    assert abs(float(loss_p) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert float((dT_p - dT).norm() / dT.norm()) <= 1e-5
+    assert float((dl_p - dl[perm.to(dev)]).norm() / dl.norm()) <= 1e-5
+    if B <= 16:
+        loss_2, dl_2, dT_2 = run(torch.cat([logits, logits]), torch.cat([labels, labels]))
+        assert abs(float(loss_2) - float(loss)) <= 1e-6 * abs(float(loss))
+        assert float((dT_2 - dT).norm() / dT.norm()) <= 1e-5
+        assert float((2 * dl_2[:B] - dl).norm() / dl.norm()) <= 1e-5
+    simt_b200.check_errors()

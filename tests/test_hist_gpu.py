@@ -127,3 +127,31 @@ def test_full_resolution_eval_image_bit_exact_miou():
     assert np.array_equal(meter.value(), ref)
     assert meter.miou_percent() == O.miou_percent(ref)
     assert int(meter.value().sum()) == int((O.label_mapping(gt, mapping) < 19).sum() * 0 + ref.sum())
+
+
+def test_config4_scale_checksums():
+    """BASELINE config 4 scale: 200 images 2048x1024 in ONE launch (0.4 G pixels): totals must equal the
+    number of gt pixels that map to a train id, row sums the per-class gt counts, and splitting the batch
+    in two launches gives the same table bit for bit."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    mapping = np.array(O.CITYSCAPES_LABEL2TRAIN)
+    base = [O.synth_eval_pair(1024, 2048, seed=70 + i, coherent=(i % 2 == 0), block=(96, 160)) for i in range(4)]
+    gt = torch.from_numpy(np.stack([b[0] for b in base])).to(dev).repeat(50, 1, 1)
+    pr = torch.from_numpy(np.stack([b[1] for b in base])).to(dev).repeat(50, 1, 1)
+    m1 = simt_b200.ConfusionMeter(19, mapping=mapping)
+    m1.update(gt, pr)
+    h1 = m1.value()
+    lut = simt_b200.build_lut(mapping).astype(np.int64)
+    gt_train = lut[np.stack([b[0] for b in base])]
+    rows = np.bincount(gt_train[gt_train < 19], minlength=19) * 50
+    assert np.array_equal(h1.sum(1), rows)
+    assert int(h1.sum()) == int((gt_train < 19).sum()) * 50
+    ref = np.zeros((19, 19), dtype=np.int64)
+    for g, p in base:
+        ref += O.fast_hist(O.label_mapping(g, mapping).flatten(), p.flatten(), 19)
+    assert np.array_equal(h1, 50 * ref)
+    m2 = simt_b200.ConfusionMeter(19, mapping=mapping)
+    m2.update(gt[:77], pr[:77]); m2.update(gt[77:], pr[77:])
+    assert np.array_equal(m2.value(), h1)
