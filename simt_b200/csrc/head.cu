@@ -352,7 +352,12 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
       const bool edge_smem = BWD && (Y1 - Y0 <= kEdgeRows);
       // ---- stage the cell's 4 corners of this lane's channels (log2 domain) in the warp's smem slice ----
       {
-        const float* src = A.logits + ((size_t)b * CK + kbase) * h * w;
+        // address arithmetic hoisted: 4 corner pointers once per cell-row, then + j * plane (one IMAD.WIDE each)
+        const unsigned plane = (unsigned)(h * w);
+        const float* q00 = A.logits + ((size_t)b * CK + kbase) * plane + (gy0 * w + gx0);
+        const float* q01 = q00 + (gx1 - gx0);
+        const float* q10 = q00 + (gy1 - gy0) * w;
+        const float* q11 = q10 + (gx1 - gx0);
         __syncwarp();
         // all 4*CPL corner loads are issued before the first one is used (one exposed L2 latency, not ten)
         float c00[CPL], c01[CPL], c10[CPL], c11[CPL];
@@ -361,9 +366,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           const float pad = cell_ok ? kPadLogit : 0.f;
           c00[j] = c01[j] = c10[j] = c11[j] = pad;
           if (cell_ok && kbase + j < CK) {
-            const float* p = src + (size_t)j * h * w;
-            c00[j] = __ldg(p + gy0 * w + gx0); c01[j] = __ldg(p + gy0 * w + gx1);
-            c10[j] = __ldg(p + gy1 * w + gx0); c11[j] = __ldg(p + gy1 * w + gx1);
+            const size_t off = (size_t)((unsigned)j * plane);
+            c00[j] = __ldg(q00 + off); c01[j] = __ldg(q01 + off);
+            c10[j] = __ldg(q10 + off); c11[j] = __ldg(q11 + off);
           }
         }
 #pragma unroll
@@ -597,15 +602,17 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
         float* dst = A.dlogits + (size_t)b * CK * h * w;
         const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
         if (cell_ok) {
-          float* dk = dst + (size_t)kbase * h * w;
+          const unsigned plane = (unsigned)(h * w);
+          float* d0 = dst + (size_t)kbase * plane + (gy0 * w + gx0);
+          float* d1 = d0 + (gy1 - gy0) * w;
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
             if (kbase + j < CK) {
-              float* pk = dk + (size_t)j * h * w;
+              const size_t off = (size_t)((unsigned)j * plane);
               const float vt = (j & 1) ? Vt[j >> 1].y : Vt[j >> 1].x;
               const float vb = (j & 1) ? Vb[j >> 1].y : Vb[j >> 1].x;
-              atomicAdd(pk + gy0 * w + gx0, vt * gs);
-              atomicAdd(pk + gy1 * w + gx0, vb * gs);
+              atomicAdd(d0 + off, vt * gs);
+              atomicAdd(d1 + off, vb * gs);
             }
           }
         }
