@@ -182,6 +182,20 @@ int simt_anchor_stats(const float* logits, int B, int CK, int h, int w, int H, i
 int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, int W,
                          const long long* pixel_idx, int n, float* rows, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Pseudo-label generation.  Replaces tools/trainV2_simt.py:354-365 (softmax of the
+ * frozen model's output2, upsample, max / arg-max, high / low confidence thresholds, and the
+ * .cpu().numpy() round trip of :362) and the class-posterior relabel of :387-393, producing the uint8
+ * label map the fused head consumes directly.
+ *   fixed_logits_lo [B, C, h, w] f32; pred2_lo [B, CK, h, w] f32 (student head 2, LOW-res) or NULL
+ *   label = arg-max class if max prob > thres_high; 255 if in between; if max prob < thres_low: the
+ *   student's arg-max class when it is an open-set class (>= C), else 255 (without pred2_lo: C itself)
+ *   probs_scratch: B*C*h*w floats.  labels_out [B, H, W] uint8.
+ * ------------------------------------------------------------------------- */
+int simt_pseudo_labels(const float* fixed_logits_lo, const float* pred2_lo, int B, int C, int CK, int h, int w,
+                       int H, int W, float thres_high, float thres_low, float* probs_scratch,
+                       uint8_t* labels_out, void* stream);
+
 /* benchmark hook (process-global): `mode` is reserved; warps per CTA and 128-bit loads in flight per lane; 0 = automatic */
 void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
 

@@ -198,6 +198,32 @@ def main():
             anchor_idx1=a_idx[0], anchor_idx2=a_idx[1], exist1=exists[0], exist2=exists[1])
         manifest["cases"].append(f"reg_K{K}")
 
+    # ---- pseudo labels + class-posterior relabel (section 8(f) row 2), executed from trainV2_simt.py:354-365,387-393 ----
+    import torch.nn as nn
+    gg = torch.Generator().manual_seed(23)
+    Bp, Cp, CKp, hp, wp, Hp, Wp = 2, 19, 23, 9, 17, 64, 128
+    output2 = 2.0 * torch.randn(Bp, Cp, hp, wp, generator=gg)
+    pred2_lo = 2.0 * torch.randn(Bp, CKp, hp, wp, generator=gg)
+    interp_target = nn.Upsample(size=(Hp, Wp), mode="bilinear", align_corners=True)
+    num_classes = 19
+    labelC = interp_target(torch.softmax(output2.clone(), dim=1))                                           # :354
+    labelC_max = torch.max(labelC, 1)                                                                        # :355
+    labelC_argmax = torch.argmax(labelC, dim=1).float()                                                      # :356
+    labelC = torch.where(labelC_max[0] > 0.8, labelC_argmax, 255. * torch.ones_like(labelC_argmax))          # :359
+    labelC = torch.where(labelC_max[0] < 0.2, num_classes * torch.ones_like(labelC_argmax), labelC)          # :361
+    Conf = torch.from_numpy(labelC.detach().clone().cpu().numpy()).long()                                    # :362
+    pred2 = interp_target(pred2_lo)                                                                          # :372
+    pseudo = torch.argmax(pred2.clone(), dim=1).detach()                                                     # :387
+    ones = torch.ones_like(Conf); zeros = torch.zeros_like(Conf)
+    mask = torch.where(Conf == num_classes * ones, ones, zeros)                                              # :390
+    pseudo1 = mask * pseudo                                                                                  # :391
+    pseudo1 = torch.where(pseudo1 >= num_classes * ones, pseudo1, 255 * ones)                                # :392
+    Conf = torch.where(Conf == num_classes * ones, pseudo1, Conf)                                            # :393
+    assert torch.equal(Conf, O.pseudo_labels(output2, pred2, (Hp, Wp), num_classes, 0.8, 0.2))
+    np.savez_compressed(os.path.join(OUT, "pseudo_K4.npz"), output2=output2.numpy(), pred2_lo=pred2_lo.numpy(),
+                        size=np.array([Hp, Wp]), conf=Conf.numpy().astype(np.uint8))
+    manifest["cases"].append("pseudo_K4")
+
     # ---- histograms (a12-a16): compute_iou's functions imported unmodified -----------------
     info = json.load(open(os.path.join(REF, "dataset", "cityscapes_list", "info.json")))
     mapping = np.array(info["label2train"], dtype=np.int64)

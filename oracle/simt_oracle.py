@@ -207,6 +207,28 @@ def label_c_flat(fixed_logits_lo: torch.Tensor, out_size) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------
+# (f) row 2: pseudo-label generation + class-posterior relabel
+# --------------------------------------------------------------------------
+def pseudo_labels(fixed_logits_lo: torch.Tensor, pred2_up: torch.Tensor, out_size, num_classes: int,
+                  thres_high: float = 0.8, thres_low: float = 0.2) -> torch.Tensor:
+    """Conf_label_target of tools/trainV2_simt.py:354-365 (threshold the frozen model's upsampled softmax) and
+    :387-393 (low-confidence pixels take the student's arg-max if that is an open-set class, else 255).
+    ``pred2_up`` is the student's UPSAMPLED head-2 logits [B, CK, H, W] (:372).  Returns int64 [B, H, W]."""
+    labelC = upsample_bilinear_ac(torch.softmax(fixed_logits_lo.clone(), dim=1), out_size)            # :354
+    labelC_max = torch.max(labelC, 1)                                                                  # :355
+    labelC_argmax = torch.argmax(labelC, dim=1).float()                                                # :356
+    lab = torch.where(labelC_max[0] > thres_high, labelC_argmax, 255. * torch.ones_like(labelC_argmax))   # :359
+    lab = torch.where(labelC_max[0] < thres_low, num_classes * torch.ones_like(labelC_argmax), lab)       # :361
+    conf = lab.long()                                                                                  # :362
+    pseudo = torch.argmax(pred2_up.clone(), dim=1).detach()                                            # :387
+    ones, zeros = torch.ones_like(conf), torch.zeros_like(conf)
+    mask = torch.where(conf == num_classes * ones, ones, zeros)                                        # :390
+    pseudo1 = mask * pseudo                                                                            # :391
+    pseudo1 = torch.where(pseudo1 >= num_classes * ones, pseudo1, 255 * ones)                          # :392
+    return torch.where(conf == num_classes * ones, pseudo1, conf)                                      # :393
+
+
+# --------------------------------------------------------------------------
 # a12 - a16: integer eval histograms (numpy, single-threaded like the reference)
 # --------------------------------------------------------------------------
 def fast_hist(a, b, n):

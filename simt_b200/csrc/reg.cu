@@ -315,3 +315,90 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// (f) row 2: pseudo-label generation, tools/trainV2_simt.py:354-365 + class-posterior relabel :387-393
+// ---------------------------------------------------------------------------------------------------
+namespace simt {
+
+// channel softmax of the frozen model's LOW-res logits (the reference applies softmax before the upsample)
+__global__ void __launch_bounds__(256) softmax_lo_kernel(const float* __restrict__ x, int B, int C, int hw,
+                                                          float* __restrict__ p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * hw) return;
+  const int b = (int)(i / hw), r = (int)(i - (long long)b * hw);
+  const float* xb = x + (size_t)b * C * hw + r;
+  float m = -INFINITY;
+  for (int k = 0; k < C; ++k) m = fmaxf(m, xb[(size_t)k * hw]);
+  float s = 0.f;
+  for (int k = 0; k < C; ++k) s += expf(xb[(size_t)k * hw] - m);
+  float* pb = p + (size_t)b * C * hw + r;
+  for (int k = 0; k < C; ++k) pb[(size_t)k * hw] = expf(xb[(size_t)k * hw] - m) / s;
+}
+
+// one pixel per thread: upsampled class posterior -> max / arg-max -> thresholds -> (student arg-max) -> uint8
+__global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ probs_lo, const float* __restrict__ pred2_lo,
+                                                            int B, int C, int CK, int h, int w, int H, int W, float sy,
+                                                            float sx, float thr_hi, float thr_lo,
+                                                            uint8_t* __restrict__ out) {
+  const long long npix = (long long)B * H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const int X = (int)(p % W);
+    const long long t = p / W;
+    const int Y = (int)(t % H);
+    const int b = (int)(t / H);
+    const Bilin bl = bilin_setup(Y, X, h, w, sy, sx);
+    const float* base = probs_lo + (size_t)b * C * h * w;
+    float best = -INFINITY;
+    int bestk = 0;
+    for (int k = 0; k < C; ++k) {
+      const float z = bilin_eval(base + (size_t)k * h * w, bl);
+      if (z > best || k == 0) { best = z; bestk = k; }
+    }
+    int lab = (best > thr_hi) ? bestk : 255;          // :359
+    if (best < thr_lo) {                               // :361 -> low confidence: :387-393
+      lab = 255;
+      if (pred2_lo) {
+        const float* pb = pred2_lo + (size_t)b * CK * h * w;
+        float sb = -INFINITY;
+        int sk = 0;
+        for (int k = 0; k < CK; ++k) {
+          const float z = bilin_eval(pb + (size_t)k * h * w, bl);
+          if (z > sb || k == 0) { sb = z; sk = k; }
+        }
+        if (sk >= C) lab = sk;                         // an open-set placeholder class
+      } else {
+        lab = C;                                       // without the student: the raw marker of :361
+      }
+    }
+    out[p] = (uint8_t)lab;
+  }
+}
+
+}  // namespace simt
+
+extern "C" int simt_pseudo_labels(const float* fixed_logits_lo, const float* pred2_lo, int B, int C, int CK, int h, int w,
+                                  int H, int W, float thres_high, float thres_low, float* probs_scratch,
+                                  uint8_t* labels_out, void* stream) {
+  using namespace simt;
+  if (!fixed_logits_lo || !probs_scratch || !labels_out) return SIMT_EINVAL;
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || C > 254) return SIMT_EINVAL;
+  if (pred2_lo && (CK < C || CK > 254)) return SIMT_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const long long nlo = (long long)B * h * w;
+  softmax_lo_kernel<<<(unsigned)((nlo + 255) / 256), 256, 0, st>>>(fixed_logits_lo, B, C, h * w, probs_scratch);
+  SIMT_CUDA_TRY(cudaGetLastError());
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  long long grid = ((long long)B * H * W + 255) / 256;
+  if (grid > (long long)di.sm_count * 16) grid = (long long)di.sm_count * 16;
+  prof_begin(st);
+  pseudo_label_kernel<<<(int)grid, 256, 0, st>>>(probs_scratch, pred2_lo, B, C, CK, h, w, H, W, sy, sx, thres_high,
+                                                 thres_low, labels_out);
+  prof_end(st);
+  return (int)cudaGetLastError();
+}

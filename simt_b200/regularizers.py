@@ -138,3 +138,28 @@ def anchor_loss(pred_lo_list: Sequence[torch.Tensor], T_list: Sequence[torch.Ten
         v = diff.pow(2).sum()                                            # :379
         tot = v if tot is None else tot + v
     return tot
+
+
+def pseudo_labels(fixed_logits_lo: torch.Tensor, pred2_lo: torch.Tensor, out_size, num_classes: int,
+                  thres_high: float = 0.8, thres_low: float = 0.2) -> torch.Tensor:
+    """``Conf_label_target`` of tools/trainV2_simt.py:354-365 + :387-393 as uint8 [B, H, W] on the device, from
+    the LOW-res outputs of the frozen model (``output2``, closed-set C channels) and of the student
+    (``pred2`` before the upsample, CK channels; may be None).  No high-res tensor, no host round trip."""
+    lib = _lib.load()
+    if not fixed_logits_lo.is_cuda:
+        raise RuntimeError("simt_b200.pseudo_labels runs on CUDA (sm_100a) only; there is no CPU fallback")
+    x = fixed_logits_lo.detach().contiguous().float()
+    B, C, h, w = x.shape
+    if C != num_classes:
+        raise ValueError(f"fixed_logits_lo has {C} channels, num_classes = {num_classes}")
+    H, W = int(out_size[0]), int(out_size[1])
+    p2 = None if pred2_lo is None else pred2_lo.detach().contiguous().float()
+    CK = C if p2 is None else p2.shape[1]
+    scratch = torch.empty_like(x)
+    out = torch.empty(B, H, W, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.simt_pseudo_labels(x.data_ptr(), None if p2 is None else p2.data_ptr(), B, C, CK, h, w, H, W,
+                                    float(thres_high), float(thres_low), scratch.data_ptr(), out.data_ptr(),
+                                    _stream_ptr())
+    _lib.check(rc, "simt_pseudo_labels")
+    return out

@@ -111,3 +111,13 @@ def test_fast_hist_aliasing_and_errors():
     assert O.fast_hist(a, np.array([0, 20, 1]), 19)[2, 1] == 2          # 19*1+20 == 19*2+1
     with pytest.raises(ValueError):
         O.fast_hist(np.array([18]), np.array([30]), 19)
+
+
+def test_pseudo_labels_rule():
+    g = load_golden("pseudo_K4")
+    size = tuple(int(s) for s in g["size"])
+    conf = O.pseudo_labels(torch.from_numpy(g["output2"]), O.upsample_bilinear_ac(torch.from_numpy(g["pred2_lo"]), size),
+                           size, 19, 0.8, 0.2)
+    assert (conf.numpy() != g["conf"]).mean() < 1e-4       # identical up to float near-ties across torch builds
+    vals = set(np.unique(g["conf"]).tolist())
+    assert 255 in vals and any(v < 19 for v in vals) and any(19 <= v < 255 for v in vals)

@@ -65,3 +65,48 @@ def test_torch_expression_forms_on_gpu():
     assert abs(float(simt_b200.convex_loss([W1, W2], [T1, T2])) - float(g["convex"])) <= TOL * abs(float(g["convex"]))
     assert abs(float(simt_b200.volume_loss([T1, T2])) - float(g["volume"])) <= TOL * abs(float(g["volume"]))
     assert abs(float(simt_b200.w_fit_loss([W1, W2], [T1, T2])) + float(g["convex"])) <= TOL * abs(float(g["convex"]))
+
+
+@pytest.mark.parametrize("K", [4, 15])
+def test_pseudo_labels_vs_oracle(K):
+    """Conf_label_target (trainV2_simt.py:354-365,387-393): identical to the oracle except at pixels that sit
+    within float rounding of a threshold or of an arg-max tie (where torch's own CPU and CUDA kernels differ)."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11 + K)
+    B, C, CK, h, w, H, W = 2, 19, 19 + K, 17, 33, 128, 256
+    fixed = 2.0 * torch.randn(B, C, h, w, generator=g)
+    pred2 = 2.0 * torch.randn(B, CK, h, w, generator=g)
+    ref = O.pseudo_labels(fixed, O.upsample_bilinear_ac(pred2, (H, W)), (H, W), C, 0.8, 0.2)
+    got = simt_b200.pseudo_labels(fixed.to(dev), pred2.to(dev), (H, W), C, 0.8, 0.2).cpu().long()
+    assert got.shape == ref.shape
+    diff = got != ref
+    # every disagreement must be explained by a near-threshold max or a near-tie of the top two
+    probs = O.upsample_bilinear_ac(torch.softmax(fixed.double(), 1), (H, W))
+    top2 = probs.topk(2, dim=1).values
+    near_thr = ((top2[:, 0] - 0.8).abs() < 1e-5) | ((top2[:, 0] - 0.2).abs() < 1e-5)
+    near_tie = (top2[:, 0] - top2[:, 1]) < 1e-5
+    s2 = O.upsample_bilinear_ac(pred2.double(), (H, W)).topk(2, dim=1).values
+    near_tie2 = (s2[:, 0] - s2[:, 1]) < 1e-5
+    assert not bool((diff & ~(near_thr | near_tie | near_tie2)).any())
+    assert float(diff.float().mean()) < 1e-3
+    # every branch of the rule is exercised
+    vals = set(ref.unique().tolist())
+    assert 255 in vals and any(v < C for v in vals) and any(C <= v < 255 for v in vals)
+    # and the labels feed the fused head directly (plain CE over CK classes, :394-395)
+    lg = pred2.to(dev).requires_grad_(True)
+    loss = simt_b200.simt_head(lg, None, simt_b200.pseudo_labels(fixed.to(dev), pred2.to(dev), (H, W), C), (H, W))
+    ref_loss = O.plain_ce_loss(pred2, ref, (H, W))
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+
+
+def test_pseudo_labels_vs_reference_golden():
+    import simt_b200
+    g = load_golden("pseudo_K4")
+    dev = torch.device("cuda")
+    size = tuple(int(s) for s in g["size"])
+    got = simt_b200.pseudo_labels(torch.from_numpy(g["output2"]).to(dev), torch.from_numpy(g["pred2_lo"]).to(dev),
+                                  size, 19, 0.8, 0.2).cpu().numpy()
+    assert got.dtype == np.uint8 and got.shape == g["conf"].shape
+    assert (got != g["conf"]).mean() < 1e-3                  # near-threshold / near-tie pixels only
