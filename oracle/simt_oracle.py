@@ -228,6 +228,28 @@ def pseudo_labels(fixed_logits_lo: torch.Tensor, pred2_up: torch.Tensor, out_siz
     return torch.where(conf == num_classes * ones, pseudo1, conf)                                      # :393
 
 
+def training_step_loss(pred1_lo, pred2_lo, fixed_out2_lo, label_target, T1, T2, W1, W2, out_size, num_classes,
+                       lambda_seg=0.1, lambda_convex=0.1, lambda_volume=1.0, lambda_anchor=1.0,
+                       thres_high=0.8, thres_low=0.2):
+    """The head part of one training iteration, tools/trainV2_simt.py:351-424, WITHOUT the backbone and
+    without Placeholder_loss (section 8(f) row 4, not built): pseudo labels (:351-365), upsample (:371-372), anchor
+    (:375-384), class-posterior relabel + seg_loss (:387-395), T-corrected losses (:402-409), convex / volume
+    (:412-421), combination (:423-424) with the published weights of sh_simt.sh:16.  B must be 1 (anchor)."""
+    up = lambda x: upsample_bilinear_ac(x, out_size)
+    labelC_flat = label_c_flat(fixed_out2_lo, out_size)
+    pred1, pred2 = up(pred1_lo), up(pred2_lo)                                                  # :371-372
+    anchor = anchor_loss([pred1, pred2], [T1, T2], labelC_flat)                                # :375-384
+    conf = pseudo_labels(fixed_out2_lo, pred2, out_size, num_classes, thres_high, thres_low)   # :354-365,387-393
+    loss_p1 = F.cross_entropy(pred1, conf, ignore_index=IGNORE_LABEL)                          # :394
+    loss_p2 = F.cross_entropy(pred2, conf, ignore_index=IGNORE_LABEL)                          # :395
+    loss_y1 = simt_head_loss(pred1_lo, T1, label_target, out_size)                             # :402-403,408
+    loss_y2 = simt_head_loss(pred2_lo, T2, label_target, out_size)                             # :405-406,409
+    convex = convex_loss([W1, W2], [T1, T2])                                                   # :412-415
+    volume = volume_loss([T1, T2])                                                             # :417-421
+    loss_target = loss_p2 + loss_y2 + lambda_seg * loss_p1 + lambda_seg * loss_y1             # :423
+    return loss_target + lambda_convex * convex + lambda_volume * volume + lambda_anchor * anchor   # :424
+
+
 # --------------------------------------------------------------------------
 # a12 - a16: integer eval histograms (numpy, single-threaded like the reference)
 # --------------------------------------------------------------------------
