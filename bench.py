@@ -209,6 +209,37 @@ def run_reference_arm(args, rank):
     }), flush=True)
 
 
+def run_torch_cuda_eager(dev, dev_set, T):
+    """The reference's own lines (tools/trainV2_simt.py:371-372,402-409 + utils/loss.py, restated in
+    oracle/simt_oracle.py) run with stock torch-CUDA eager kernels on THIS GPU, same batch: the bar the
+    reference's users see today (it trains on a GPU).  fwd + autograd bwd, CUDA events, 10 steps."""
+    from oracle import simt_oracle as O
+    lg, lab = dev_set
+    lab64 = lab.long()
+
+    def one():
+        x = lg.detach().clone().requires_grad_(True)
+        Tt = T.detach().clone().requires_grad_(True)
+        loss = O.simt_head_loss(x, Tt, lab64, (H, W))
+        loss.backward()
+        return loss
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    labeled = int((lab != 255).sum())
+    return {"value": labeled / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "what": "reference lines on torch-CUDA eager (upsample, softmax, permute, mm, mask gather, log, nll, autograd)",
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+
+
 def run_eval_confusion(lib, dev):
     """BASELINE configs[3] (secondary, same JSON line): int64 19x19 confusion matrix of 500 synthetic
     2048x1024 val images (raw Cityscapes ids through the label2train LUT vs uint8 predictions), two
@@ -388,6 +419,7 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:
             out["cpu_baseline"] = run_cpu_baseline()
             out["eval_confusion"] = run_eval_confusion(lib, dev)
+            out["torch_cuda_eager"] = run_torch_cuda_eager(dev, sets[0], T)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
