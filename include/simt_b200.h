@@ -196,6 +196,16 @@ int simt_pseudo_labels(const float* fixed_logits_lo, const float* pred2_lo, int 
                        int H, int W, float thres_high, float thres_low, float* probs_scratch,
                        uint8_t* labels_out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Fused eval prediction map.  Replaces tools/evaluate_cityscapes.py:127-138
+ * (evaluate_simt: upsample the closed-set channels of output2 of the 1024x512 pass and of the 1280x640
+ * pass to the label size, two 159 MB device->host copies per image, add, np.argmax) and :186-196
+ * (evaluate_warmup, one scale: logits_b = NULL).  pred_out [B, H, W] uint8 feeds simt_confusion.
+ *   logits_a [B, CKa, ha, wa], logits_b [B, CKb, hb, wb] or NULL; the first C channels are used.
+ * ------------------------------------------------------------------------- */
+int simt_eval_argmax(const float* logits_a, int CKa, int ha, int wa, const float* logits_b, int CKb, int hb, int wb,
+                     int B, int C, int H, int W, uint8_t* pred_out, void* stream);
+
 /* benchmark hook (process-global): `mode` is reserved; warps per CTA and 128-bit loads in flight per lane; 0 = automatic */
 void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
 

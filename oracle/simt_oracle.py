@@ -228,6 +228,20 @@ def pseudo_labels(fixed_logits_lo: torch.Tensor, pred2_up: torch.Tensor, out_siz
     return torch.where(conf == num_classes * ones, pseudo1, conf)                                      # :393
 
 
+def eval_two_scale_argmax(out2_a: torch.Tensor, out2_b, out_size, num_classes: int) -> np.ndarray:
+    """Prediction map of tools/evaluate_cityscapes.py:127-138 (``evaluate_simt``): head-2 logits of the 1024x512
+    pass and of the 1280x640 pass, closed-set channels only, each upsampled to the label size, added in float32
+    on the host, arg-max over classes.  ``out2_b`` may be None (``evaluate_warmup``, :186-196).  uint8 [B, H, W]."""
+    outs = []
+    for i in range(out2_a.shape[0]):
+        output = upsample_bilinear_ac(out2_a[i:i + 1, :num_classes], out_size).cpu().data[0].numpy()      # :128
+        if out2_b is not None:
+            output += upsample_bilinear_ac(out2_b[i:i + 1, :num_classes], out_size).cpu().data[0].numpy()  # :133
+        output = output.transpose(1, 2, 0)                                                                 # :137
+        outs.append(np.asarray(np.argmax(output, axis=2)))                                                 # :138
+    return np.stack(outs).astype(np.uint8)
+
+
 def training_step_loss(pred1_lo, pred2_lo, fixed_out2_lo, label_target, T1, T2, W1, W2, out_size, num_classes,
                        lambda_seg=0.1, lambda_convex=0.1, lambda_volume=1.0, lambda_anchor=1.0,
                        thres_high=0.8, thres_low=0.2):

@@ -42,6 +42,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "simt_pseudo_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                    c_void_p, c_void_p, c_void_p]),
+    "simt_eval_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p]),
     "simt_bilinear_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                      c_void_p]),
 }

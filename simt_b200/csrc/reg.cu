@@ -402,3 +402,61 @@ extern "C" int simt_pseudo_labels(const float* fixed_logits_lo, const float* pre
   prof_end(st);
   return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// (f) row 3: fused eval prediction map, tools/evaluate_cityscapes.py:127-138 (two-scale) / :186-196 (one scale)
+// ---------------------------------------------------------------------------------------------------
+namespace simt {
+
+__global__ void __launch_bounds__(256) eval_argmax_kernel(const float* __restrict__ la, int CKa, int ha, int wa,
+                                                           const float* __restrict__ lb, int CKb, int hb, int wb, int B,
+                                                           int C, int H, int W, float sya, float sxa, float syb,
+                                                           float sxb, uint8_t* __restrict__ pred) {
+  const long long npix = (long long)B * H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+    const int X = (int)(p % W);
+    const long long t = p / W;
+    const int Y = (int)(t % H);
+    const int b = (int)(t / H);
+    const Bilin ba = bilin_setup(Y, X, ha, wa, sya, sxa);
+    const float* pa = la + (size_t)b * CKa * ha * wa;
+    Bilin bb = ba;
+    const float* pb = nullptr;
+    if (lb) {
+      bb = bilin_setup(Y, X, hb, wb, syb, sxb);
+      pb = lb + (size_t)b * CKb * hb * wb;
+    }
+    float best = -INFINITY;
+    int bestk = 0;
+    for (int k = 0; k < C; ++k) {
+      float z = bilin_eval(pa + (size_t)k * ha * wa, ba);
+      if (pb) z = __fadd_rn(z, bilin_eval(pb + (size_t)k * hb * wb, bb));   // the reference adds in fp32 on the host
+      if (z > best || k == 0) { best = z; bestk = k; }                       // first maximum, like np.argmax
+    }
+    pred[p] = (uint8_t)bestk;
+  }
+}
+
+}  // namespace simt
+
+extern "C" int simt_eval_argmax(const float* logits_a, int CKa, int ha, int wa, const float* logits_b, int CKb, int hb,
+                                int wb, int B, int C, int H, int W, uint8_t* pred_out, void* stream) {
+  using namespace simt;
+  if (!logits_a || !pred_out || B <= 0 || C <= 0 || C > 255 || CKa < C || ha <= 0 || wa <= 0 || H <= 0 || W <= 0)
+    return SIMT_EINVAL;
+  if (logits_b && (CKb < C || hb <= 0 || wb <= 0)) return SIMT_EINVAL;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  auto sc = [](int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; };
+  long long grid = ((long long)B * H * W + 255) / 256;
+  if (grid > (long long)di.sm_count * 16) grid = (long long)di.sm_count * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  eval_argmax_kernel<<<(int)grid, 256, 0, st>>>(logits_a, CKa, ha, wa, logits_b, CKb, hb, wb, B, C, H, W, sc(ha, H),
+                                                sc(wa, W), logits_b ? sc(hb, H) : 0.f, logits_b ? sc(wb, W) : 0.f,
+                                                pred_out);
+  prof_end(st);
+  return (int)cudaGetLastError();
+}

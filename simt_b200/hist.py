@@ -153,3 +153,24 @@ class ConfusionMeter:
     def miou_percent(self) -> float:
         """``round(np.nanmean(mIoUs) * 100, 2)`` (compute_iou.py:58)."""
         return round(float(np.nanmean(self.per_class_iu())) * 100, 2)
+
+
+def eval_argmax(logits_a: torch.Tensor, logits_b: torch.Tensor, out_size, num_classes: int) -> torch.Tensor:
+    """uint8 prediction map [B, H, W] of tools/evaluate_cityscapes.py:127-138: upsample the first
+    ``num_classes`` channels of one (``logits_b=None``) or two low-res head-2 outputs to ``out_size``, add,
+    arg-max -- on the device, without the reference's two 159 MB device->host copies per image.  Feed it to
+    ``ConfusionMeter.update(gt, pred)``."""
+    lib = _lib.load()
+    if not logits_a.is_cuda:
+        raise RuntimeError("simt_b200.eval_argmax runs on CUDA (sm_100a) only; there is no CPU fallback")
+    a = logits_a.detach().contiguous().float()
+    b = None if logits_b is None else logits_b.detach().contiguous().float()
+    B, CKa, ha, wa = a.shape
+    H, W = int(out_size[0]), int(out_size[1])
+    out = torch.empty(B, H, W, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.simt_eval_argmax(a.data_ptr(), CKa, ha, wa, None if b is None else b.data_ptr(),
+                                  0 if b is None else b.shape[1], 0 if b is None else b.shape[2],
+                                  0 if b is None else b.shape[3], B, int(num_classes), H, W, out.data_ptr(), _stream_ptr())
+    _lib.check(rc, "simt_eval_argmax")
+    return out

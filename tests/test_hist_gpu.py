@@ -155,3 +155,34 @@ def test_config4_scale_checksums():
     m2 = simt_b200.ConfusionMeter(19, mapping=mapping)
     m2.update(gt[:77], pr[:77]); m2.update(gt[77:], pr[77:])
     assert np.array_equal(m2.value(), h1)
+
+
+@pytest.mark.parametrize("two_scale", [True, False])
+def test_fused_eval_argmax_and_miou(two_scale):
+    """evaluate_cityscapes.py:127-148 on synthetic logits: the fused prediction map equals the oracle's except at
+    arg-max near-ties (float op order of the upsample), and the resulting confusion matrix differs by at most
+    those pixels."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 256, 512
+    a = 3.0 * torch.randn(B, 34, 33, 65, generator=g)              # open-set head: only the first 19 channels count
+    b = 3.0 * torch.randn(B, 34, 41, 81, generator=g) if two_scale else None
+    ref = O.eval_two_scale_argmax(a, b, (H, W), 19)
+    got = simt_b200.eval_argmax(a.to(dev), None if b is None else b.to(dev), (H, W), 19).cpu().numpy()
+    diff = got != ref
+    z = O.upsample_bilinear_ac(a[:, :19].double(), (H, W))
+    if b is not None:
+        z = z + O.upsample_bilinear_ac(b[:, :19].double(), (H, W))
+    top2 = z.topk(2, dim=1).values
+    near_tie = ((top2[:, 0] - top2[:, 1]) < 1e-4).numpy()
+    assert not (diff & ~near_tie).any()
+    assert diff.mean() < 1e-3
+    gt, _ = O.synth_eval_pair(B * H, W, seed=1, block=(24, 40))
+    gt = gt.reshape(B, H, W)
+    m = simt_b200.ConfusionMeter(19, mapping=O.CITYSCAPES_LABEL2TRAIN)
+    m.update(gt, torch.from_numpy(got).to(dev))
+    lab = O.label_mapping(gt, np.array(O.CITYSCAPES_LABEL2TRAIN))
+    ref_hist = O.fast_hist(lab.flatten(), ref.flatten().astype(np.int64), 19)
+    assert np.abs(m.value() - ref_hist).sum() <= 2 * int(diff.sum())
