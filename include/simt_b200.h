@@ -183,6 +183,22 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
                          const long long* pixel_idx, int n, float* rows, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Inner W optimisation (tools/trainV2_simt.py:326-339), one head, ONE single-CTA launch.
+ * Runs n_steps rounds of: W = softmax(weight with diag := -1e4, dim 1) - I
+ * (model/deeplab_multi.py:277-286), loss = sum((W T)^2) (:336), backward (:337), and a
+ * torch.optim.Adam step (no weight decay, no amsgrad) on `weight` (:338-339).
+ *   weight, exp_avg, exp_avg_sq [CK, CK] f32: updated IN PLACE (the optimiser's state tensors)
+ *   T [CK, C] f32: constant during the loop
+ *   step0: Adam steps already taken on `weight` (state['step']); lr/beta1/beta2/eps: the param group's
+ *   dT_accum [CK, C] f32 or NULL: += sum over the rounds of dLoss/dT (the reference's backward at
+ *     :337 accumulates into NTM.grad ten times before optimizer_t.step() at :432)
+ *   losses [n_steps] f32 or NULL: the objective at the start of each round
+ * ------------------------------------------------------------------------- */
+int simt_w_fit(float* weight, float* exp_avg, float* exp_avg_sq, const float* T, int CK, int C,
+               int n_steps, long long step0, double lr, double beta1, double beta2, double eps,
+               float* dT_accum, float* losses, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Pseudo-label generation.  Replaces tools/trainV2_simt.py:354-365 (softmax of the
  * frozen model's output2, upsample, max / arg-max, high / low confidence thresholds, and the
  * .cpu().numpy() round trip of :362) and the class-posterior relabel of :387-393, producing the uint8

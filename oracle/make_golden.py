@@ -78,12 +78,73 @@ HEAD_CASES = [
 ]
 
 
+def close(x, y, what, tol):
+    x, y = torch.as_tensor(x).double(), torch.as_tensor(y).double()
+    err, ref = float((x - y).norm()), float(y.norm())
+    assert err <= tol * max(ref, 1e-30), f"{what}: restatement differs from the reference ({err:.3e} vs norm {ref:.3e})"
+
+
+def gen_wfit(sig_NTM, sig_W, O, manifest):
+    # ---- inner W optimisation (a8), trainV2_simt.py:271-280,317-339 with the reference's modules + torch Adam ----
+    for K in (4, 15):
+        CK = 19 + K
+        torch.manual_seed(777 + K)
+        ntm = [sig_NTM(19, K), sig_NTM(19, K)]
+        wm = [sig_W(19, K), sig_W(19, K)]
+        lr = 2.5e-4                                                                      # LEARNING_RATE_T (:48)
+        opt_t = [torch.optim.Adam(m.parameters(), lr=lr, weight_decay=0) for m in ntm]  # :271,274
+        opt_w = [torch.optim.Adam(m.parameters(), lr=lr, weight_decay=0) for m in wm]   # :277,280
+        loss_mse = torch.nn.MSELoss(reduction="sum")
+        zeros = torch.zeros(CK, 19)
+        # oracle twin, from the same initial state
+        o_ntm = [m.NTM.detach().clone() for m in ntm]
+        o_w = [m.weight.detach().clone() for m in wm]
+        o_st = [dict(m=torch.zeros(CK, CK), v=torch.zeros(CK, CK), step=0) for _ in wm]
+        cd = np.load(os.path.join(REF, "ClassDist", "ClassDist_bapa.npy"))
+        out = dict(ntm1=o_ntm[0].numpy().copy(), ntm2=o_ntm[1].numpy().copy(), w1_init=o_w[0].numpy().copy(),
+                   w2_init=o_w[1].numpy().copy(), lr=np.float64(lr), rounds=np.int64(10))
+        for outer in range(2):                      # two outer iterations: the second starts from Adam step 10
+            for o in opt_t + opt_w:
+                o.zero_grad()                                                            # :317-320
+            ref_losses = []
+            for it in range(10):                                                         # :327
+                T1, T2, W1, W2 = ntm[0](), ntm[1](), wm[0](), wm[1]()                    # :329-332
+                opt_w[0].zero_grad(); opt_w[1].zero_grad()                               # :333-334
+                NTM_loss = loss_mse(W1.mm(T1), zeros) + loss_mse(W2.mm(T2), zeros)       # :336
+                NTM_loss.backward(retain_graph=True)                                     # :337
+                opt_w[0].step(); opt_w[1].step()                                         # :338-339
+                ref_losses.append(NTM_loss.detach())
+            g_o, l_o = O.w_fit_loop(o_ntm, o_w, o_st, lr, cd, 19, K, rounds=10)
+            for i in range(2):
+                stt = opt_w[i].state[wm[i].weight]
+                assert int(stt["step"]) == o_st[i]["step"] == 10 * (outer + 1)
+                close(o_w[i], wm[i].weight.detach(), f"wfit K{K} weight{i} outer{outer}", tol=1e-6)
+                close(o_st[i]["m"], stt["exp_avg"], f"wfit K{K} exp_avg{i}", tol=1e-5)
+                close(o_st[i]["v"], stt["exp_avg_sq"], f"wfit K{K} exp_avg_sq{i}", tol=1e-5)
+                close(g_o[i], ntm[i].NTM.grad, f"wfit K{K} ntm grad{i}", tol=1e-5)
+                out[f"w{i + 1}_after{outer}"] = wm[i].weight.detach().numpy().copy()
+                out[f"m{i + 1}_after{outer}"] = stt["exp_avg"].numpy().copy()
+                out[f"v{i + 1}_after{outer}"] = stt["exp_avg_sq"].numpy().copy()
+                out[f"ntm_grad{i + 1}_outer{outer}"] = ntm[i].NTM.grad.numpy().copy()
+            close(l_o, torch.stack(ref_losses), f"wfit K{K} losses", tol=1e-5)
+            out[f"losses_outer{outer}"] = torch.stack(ref_losses).numpy()
+        np.savez_compressed(os.path.join(OUT, f"wfit_K{K}.npz"), **out)
+        manifest["cases"].append(f"wfit_K{K}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     CrossEntropy2d, sig_NTM, sig_W, compute_iou = _import_reference()
     from oracle import simt_oracle as O
 
     manifest = {"torch": torch.__version__, "numpy": np.__version__, "cases": []}
+    if sys.argv[1:] == ["--only", "wfit"]:      # add / refresh the wfit cases without touching the other fixtures
+        manifest = json.load(open(os.path.join(OUT, "MANIFEST.json")))
+        manifest["cases"] = [c for c in manifest["cases"] if not c.startswith("wfit_")]
+        gen_wfit(sig_NTM, sig_W, O, manifest)
+        json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
+        print("wrote wfit cases;", len(manifest["cases"]), "golden cases in", OUT)
+        return
     class_dist = np.load(os.path.join(REF, "ClassDist", "ClassDist_bapa.npy"))
     np.save(os.path.join(OUT, "ClassDist_bapa.npy"), class_dist)
 
@@ -197,6 +258,8 @@ def main():
             p1=p1.numpy(), p2=p2.numpy(), fixed=fx.numpy(), size=np.array([H, W]),
             anchor_idx1=a_idx[0], anchor_idx2=a_idx[1], exist1=exists[0], exist2=exists[1])
         manifest["cases"].append(f"reg_K{K}")
+
+    gen_wfit(sig_NTM, sig_W, O, manifest)
 
     # ---- pseudo labels + class-posterior relabel (section 8(f) row 2), executed from trainV2_simt.py:354-365,387-393 ----
     import torch.nn as nn

@@ -165,6 +165,61 @@ def w_fit_loss(W_list, T_list) -> torch.Tensor:
     return -convex_loss(W_list, T_list)
 
 
+def adam_step(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8):
+    """One torch.optim.Adam update (weight_decay 0, amsgrad off), in place on p / m / v; ``step`` is the 1-based
+    count AFTER this update.  torch (third-party, torch/optim/adam.py ``_single_tensor_adam``) is the reference's
+    optimiser at trainV2_simt.py:277-280; this restates its published algorithm."""
+    b1, b2 = betas
+    m.lerp_(g, 1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+def w_fit_loop(ntm_params, weights, states, lr, class_dist, num_classes, open_classes, rounds=10):
+    """The inner W optimisation, trainV2_simt.py:326-339, for any number of heads.
+
+    ntm_params: list of sig_NTM.NTM tensors (not stepped here); weights: list of sig_W.weight tensors, updated in
+    place; states: list of dicts {m, v, step} (Adam state of each weight), updated in place.
+    Returns (ntm_grads, losses): the gradient the ``rounds`` backward passes of :337 ACCUMULATE into each NTM
+    parameter (zeroed once per outer iteration at :317-318), and the objective of :336 at every round."""
+    ntm_grads = [torch.zeros_like(p) for p in ntm_params]
+    losses = []
+    for _ in range(rounds):
+        leaves_n = [p.detach().clone().requires_grad_(True) for p in ntm_params]
+        leaves_w = [w.detach().clone().requires_grad_(True) for w in weights]
+        Ts = [sig_ntm_forward(p, class_dist, num_classes, open_classes) for p in leaves_n]      # :328-329
+        Ws = [sig_w_forward_functional(w) for w in leaves_w]                                     # :330-331
+        loss = w_fit_loss(Ws, Ts)                                                                # :336
+        loss.backward()                                                                          # :337
+        losses.append(loss.detach())
+        for i, w in enumerate(weights):
+            ntm_grads[i] += leaves_n[i].grad
+            st = states[i]
+            st["step"] += 1
+            with torch.no_grad():
+                w.copy_(_fill_diag(w))                    # sig_W.forward's in-place diagonal write (:279-281)
+                adam_step(w, leaves_w[i].grad, st["m"], st["v"], st["step"], lr)               # :338-339
+    return ntm_grads, torch.stack(losses)
+
+
+def _fill_diag(w):
+    out = w.clone()
+    out.fill_diagonal_(-10000.0)
+    return out
+
+
+def sig_w_forward_functional(weight: torch.Tensor) -> torch.Tensor:
+    """``sig_w_forward`` without the in-place write: the diagonal is masked to -1e4 (no gradient reaches it,
+    like the reference, whose softmax output is exactly 0 there)."""
+    n = weight.shape[0]
+    eye = torch.eye(n, dtype=torch.bool)
+    w = torch.softmax(torch.where(eye, torch.full_like(weight, -10000.0), weight), dim=1)
+    return w - torch.eye(n, dtype=weight.dtype)
+
+
 def volume_loss(T_list):
     """sum_heads log sqrt |det(T^T T)|; inf/nan -> python 0.  trainV2_simt.py:417-421."""
     tot = None

@@ -140,6 +140,71 @@ def anchor_loss(pred_lo_list: Sequence[torch.Tensor], T_list: Sequence[torch.Ten
     return tot
 
 
+def w_fit(weight: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, T: torch.Tensor, n_steps: int,
+          step0: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, dT_accum: torch.Tensor | None = None,
+          losses: torch.Tensor | None = None) -> None:
+    """``n_steps`` rounds of (sig_W forward, ``||W T||^2``, backward, Adam step) in ONE launch, all in place
+    (trainV2_simt.py:326-339 for one head; see ``simt_w_fit`` in include/simt_b200.h)."""
+    lib = _lib.load()
+    ck, c = T.shape
+    for name, t, shape in (("weight", weight, (ck, ck)), ("exp_avg", exp_avg, (ck, ck)),
+                           ("exp_avg_sq", exp_avg_sq, (ck, ck)), ("T", T, (ck, c)), ("dT_accum", dT_accum, (ck, c)),
+                           ("losses", losses, (n_steps,))):
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise ValueError(f"w_fit: {name} must be a contiguous CUDA float32 tensor of shape {shape}")
+    _lib.check(lib.simt_w_fit(weight.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), T.data_ptr(), ck, c,
+                              int(n_steps), int(step0), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                              dT_accum.data_ptr() if dT_accum is not None else None,
+                              losses.data_ptr() if losses is not None else None, _stream_ptr()), "simt_w_fit")
+
+
+def fit_w(ntm: torch.nn.Module, w_module: torch.nn.Module, optimizer: torch.optim.Optimizer, steps: int = 10,
+          accumulate_t_grad: bool = True, return_losses: bool = False):
+    """The reference's inner loop ``for iter in range(10): ... optimizer_w.step()`` (trainV2_simt.py:326-339)
+    for ONE head: ``fit_w(NTM1, NTM_W1, optimizer_w1)``.  ``optimizer`` must be the ``torch.optim.Adam`` that owns
+    ``w_module.weight`` (:277); its ``exp_avg`` / ``exp_avg_sq`` / ``step`` state is read and advanced exactly as
+    ``steps`` calls of ``optimizer.step()`` would, and ``w_module.weight.grad`` is left zeroed-equivalent (None).
+    With ``accumulate_t_grad`` the T-side gradient of the ``steps`` backward passes is accumulated into
+    ``ntm.NTM.grad`` as the reference's ``NTM_loss.backward(retain_graph=True)`` (:337) does.
+    Returns the per-round objectives (device tensor) when ``return_losses``."""
+    p = w_module.weight
+    if not isinstance(optimizer, torch.optim.Adam):
+        raise TypeError("fit_w: the fused inner loop implements torch.optim.Adam (trainV2_simt.py:277)")
+    group = next((g for g in optimizer.param_groups if any(q is p for q in g["params"])), None)
+    if group is None:
+        raise ValueError("fit_w: optimizer does not own w_module.weight")
+    if group.get("amsgrad") or group.get("weight_decay", 0) != 0 or group.get("maximize"):
+        raise NotImplementedError("fit_w: amsgrad / weight_decay / maximize are not used by the reference")
+    if not p.is_cuda:
+        raise RuntimeError("fit_w: CUDA only (no CPU fallback)")
+    state = optimizer.state[p]
+    if len(state) == 0:
+        state["step"] = torch.tensor(0.0, dtype=torch.float32)
+        state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    step0 = int(state["step"].item()) if torch.is_tensor(state["step"]) else int(state["step"])
+    lr = group["lr"]
+    lr = float(lr.item()) if torch.is_tensor(lr) else float(lr)
+    T = ntm()
+    Td = T.detach().contiguous()
+    want_t = accumulate_t_grad and T.requires_grad
+    dT = torch.zeros_like(Td) if want_t else None
+    losses = torch.empty(steps, dtype=torch.float32, device=p.device) if return_losses else None
+    with torch.no_grad():
+        w_fit(p.data, state["exp_avg"], state["exp_avg_sq"], Td, steps, step0, lr, group["betas"], group["eps"],
+              dT_accum=dT, losses=losses)
+    if torch.is_tensor(state["step"]):
+        state["step"] += steps
+    else:
+        state["step"] = step0 + steps
+    p.grad = None
+    if want_t:
+        T.backward(dT)
+    return losses
+
+
 def pseudo_labels(fixed_logits_lo: torch.Tensor, pred2_lo: torch.Tensor, out_size, num_classes: int,
                   thres_high: float = 0.8, thres_low: float = 0.2) -> torch.Tensor:
     """``Conf_label_target`` of tools/trainV2_simt.py:354-365 + :387-393 as uint8 [B, H, W] on the device, from

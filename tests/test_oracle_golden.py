@@ -121,3 +121,26 @@ def test_pseudo_labels_rule():
     assert (conf.numpy() != g["conf"]).mean() < 1e-4       # identical up to float near-ties across torch builds
     vals = set(np.unique(g["conf"]).tolist())
     assert 255 in vals and any(v < 19 for v in vals) and any(19 <= v < 255 for v in vals)
+
+
+@pytest.mark.parametrize("K", [4, 15])
+def test_inner_w_loop_matches_reference(K):
+    """trainV2_simt.py:326-339 (10 rounds of sig_W forward, ||W T||^2, backward, torch Adam), two outer
+    iterations, against weights / Adam state / accumulated NTM grads recorded from the reference's modules."""
+    g = load_golden(f"wfit_K{K}")
+    CK = 19 + K
+    cd = np.load(os.path.join(GOLDEN, "ClassDist_bapa.npy"))
+    ntm = [torch.from_numpy(g["ntm1"]).clone(), torch.from_numpy(g["ntm2"]).clone()]
+    w = [torch.from_numpy(g["w1_init"]).clone(), torch.from_numpy(g["w2_init"]).clone()]
+    st = [dict(m=torch.zeros(CK, CK), v=torch.zeros(CK, CK), step=0) for _ in range(2)]
+    off = ~np.eye(CK, dtype=bool)
+    for outer in range(2):
+        grads, losses = O.w_fit_loop(ntm, w, st, float(g["lr"]), cd, 19, K, rounds=int(g["rounds"]))
+        assert _close(losses.numpy(), g[f"losses_outer{outer}"], 1e-5)
+        for i in range(2):
+            assert st[i]["step"] == 10 * (outer + 1)
+            assert np.all(w[i].numpy()[~off] == -10000.0)
+            assert _close(w[i].numpy()[off], g[f"w{i + 1}_after{outer}"][off], 1e-6)
+            assert _close(st[i]["m"].numpy(), g[f"m{i + 1}_after{outer}"], 1e-5)
+            assert _close(st[i]["v"].numpy(), g[f"v{i + 1}_after{outer}"], 1e-5)
+            assert _close(grads[i].numpy(), g[f"ntm_grad{i + 1}_outer{outer}"], 1e-5)

@@ -110,3 +110,110 @@ def test_pseudo_labels_vs_reference_golden():
                                   size, 19, 0.8, 0.2).cpu().numpy()
     assert got.dtype == np.uint8 and got.shape == g["conf"].shape
     assert (got != g["conf"]).mean() < 1e-3                  # near-threshold / near-tie pixels only
+
+
+def _adam_weight_ok(w, ref, v_ref, lr, steps, off):
+    """|w - ref| <= TOL*|ref| + steps*lr*G/(sqrt(v)+eps): Adam divides by sqrt(v), so where the gradient itself is at the
+    fp32 rounding floor G (~1e-6 of a typical |g| ~ 1e-4) the update is ill-conditioned -- torch's own CUDA run
+    differs from its CPU run by 1.1e-4 relative at such an element (K=4, head 2), everywhere else by < 1e-6."""
+    G = 2e-10
+    tol = TOL * np.abs(ref) + steps * lr * G / (np.sqrt(v_ref) + 1e-8)
+    return bool(np.all(np.abs(w - ref)[off] <= tol[off]))
+
+
+def _wfit_modules(g, K, dev):
+    import simt_b200
+    ntm = [simt_b200.sig_NTM(19, K).to(dev) for _ in range(2)]
+    wm = [simt_b200.sig_W(19, K).to(dev) for _ in range(2)]
+    with torch.no_grad():
+        for i in range(2):
+            ntm[i].NTM.copy_(torch.from_numpy(g[f"ntm{i + 1}"]))
+            wm[i].weight.copy_(torch.from_numpy(g[f"w{i + 1}_init"]))
+    lr = float(g["lr"])
+    opt_t = [torch.optim.Adam(m.parameters(), lr=lr, weight_decay=0) for m in ntm]
+    opt_w = [torch.optim.Adam(m.parameters(), lr=lr, weight_decay=0) for m in wm]
+    return ntm, wm, opt_t, opt_w
+
+
+@pytest.mark.parametrize("K", [4, 15])
+def test_fused_inner_w_loop_vs_reference_golden(K):
+    """fit_w (ONE launch per head) against the reference's own 10-round loop with torch Adam
+    (trainV2_simt.py:326-339), two outer iterations so that the Adam state carries over."""
+    import simt_b200
+    g = load_golden(f"wfit_K{K}")
+    CK = 19 + K
+    dev = torch.device("cuda")
+    ntm, wm, opt_t, opt_w = _wfit_modules(g, K, dev)
+    off = ~np.eye(CK, dtype=bool)
+    for outer in range(2):
+        for o in opt_t + opt_w:
+            o.zero_grad()
+        losses = [simt_b200.fit_w(ntm[i], wm[i], opt_w[i], steps=10, return_losses=True) for i in range(2)]
+        tot = (losses[0] + losses[1]).cpu().numpy()
+        assert rel_max(tot, g[f"losses_outer{outer}"]) <= TOL
+        for i in range(2):
+            st = opt_w[i].state[wm[i].weight]
+            assert int(st["step"]) == 10 * (outer + 1)
+            wgt = wm[i].weight.detach().cpu().numpy()
+            ref = g[f"w{i + 1}_after{outer}"]
+            assert np.all(wgt[~off] == -10000.0)
+            assert _adam_weight_ok(wgt, ref, g[f"v{i + 1}_after{outer}"], float(g["lr"]), 10 * (outer + 1), off), (outer, i)
+            # the UPDATE itself (a few 1e-3), not just the weight it is added to
+            upd, upd_ref = wgt[off] - g[f"w{i + 1}_init"][off], ref[off] - g[f"w{i + 1}_init"][off]
+            assert rel_l2(upd, upd_ref) <= 2e-4, (outer, i)
+            assert rel_l2(st["exp_avg"].cpu().numpy(), g[f"m{i + 1}_after{outer}"]) <= TOL
+            assert rel_l2(st["exp_avg_sq"].cpu().numpy(), g[f"v{i + 1}_after{outer}"]) <= TOL
+            assert rel_l2(ntm[i].NTM.grad.cpu().numpy(), g[f"ntm_grad{i + 1}_outer{outer}"]) <= TOL
+
+
+def test_fused_inner_w_loop_vs_live_torch_adam():
+    """Same comparison against torch.optim.Adam running the literal loop on the GPU, from a perturbed start
+    and with a decayed learning rate (adjust_learning_rate_T, :183-186)."""
+    import simt_b200
+    K, dev = 15, torch.device("cuda")
+    g = load_golden(f"wfit_K{K}")
+    a = _wfit_modules(g, K, dev)
+    b = _wfit_modules(g, K, dev)
+    gen = torch.Generator().manual_seed(3)
+    for i in range(2):
+        noise = 0.2 * torch.randn(19 + K, 19 + K, generator=gen)
+        with torch.no_grad():
+            a[1][i].weight.add_(noise.to(dev)); b[1][i].weight.add_(noise.to(dev))
+    mse = torch.nn.MSELoss(reduction="sum")
+    zeros = torch.zeros(19 + K, 19, device=dev)
+    for outer, lr in enumerate((2.5e-4, 1.7e-4, 0.9e-4)):
+        for o in a[2] + a[3] + b[2] + b[3]:
+            o.zero_grad()
+            for pg in o.param_groups:
+                pg["lr"] = lr
+        for _ in range(10):                                     # literal reference loop on (a)
+            T1, T2, W1, W2 = a[0][0](), a[0][1](), a[1][0](), a[1][1]()
+            a[3][0].zero_grad(); a[3][1].zero_grad()
+            loss = mse(W1.mm(T1), zeros) + mse(W2.mm(T2), zeros)
+            loss.backward(retain_graph=True)
+            a[3][0].step(); a[3][1].step()
+        for i in range(2):                                      # fused on (b)
+            simt_b200.fit_w(b[0][i], b[1][i], b[3][i], steps=10)
+        off = ~torch.eye(19 + K, dtype=torch.bool, device=dev)
+        for i in range(2):
+            wa, wb = a[1][i].weight.detach(), b[1][i].weight.detach()
+            sa = a[3][i].state[a[1][i].weight]
+            assert _adam_weight_ok(wb.cpu().numpy(), wa.cpu().numpy(), sa["exp_avg_sq"].cpu().numpy(), 2.5e-4,
+                                   10 * (outer + 1), off.cpu().numpy()), (outer, i)
+            assert rel_l2(b[0][i].NTM.grad.cpu().numpy(), a[0][i].NTM.grad.cpu().numpy()) <= TOL
+            sa, sb = a[3][i].state[a[1][i].weight], b[3][i].state[b[1][i].weight]
+            assert int(sa["step"]) == int(sb["step"]) == 10 * (outer + 1)
+            assert rel_l2(sb["exp_avg"].cpu().numpy(), sa["exp_avg"].cpu().numpy()) <= TOL
+            assert rel_l2(sb["exp_avg_sq"].cpu().numpy(), sa["exp_avg_sq"].cpu().numpy()) <= TOL
+
+
+def test_fit_w_rejects_what_it_does_not_implement():
+    import simt_b200
+    dev = torch.device("cuda")
+    ntm, wm = simt_b200.sig_NTM(19, 4).to(dev), simt_b200.sig_W(19, 4).to(dev)
+    with pytest.raises(TypeError):
+        simt_b200.fit_w(ntm, wm, torch.optim.SGD(wm.parameters(), lr=0.1))
+    with pytest.raises(NotImplementedError):
+        simt_b200.fit_w(ntm, wm, torch.optim.Adam(wm.parameters(), lr=0.1, weight_decay=0.01))
+    with pytest.raises(ValueError):
+        simt_b200.fit_w(ntm, wm, torch.optim.Adam(ntm.parameters(), lr=0.1))
