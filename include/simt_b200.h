@@ -183,6 +183,27 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
                          const long long* pixel_idx, int n, float* rows, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Placeholder_loss (tools/trainV2_simt.py:202-230, called at :398-399 on the
+ * upsampled prediction of :371-372), fused with the bilinear upsample and its backward like the head:
+ * the [B, CK, H, W] tensor, its one-hot, `predict`, `predict_open` and their gradients are never
+ * materialised.  Per upsampled pixel, with a = arg-max channel (first on ties):
+ *   valid   iff a < C (a known class) and (thres < 0 or max softmax prob > thres)            (:213-216)
+ *   known   = -log softmax(z)_a                                                                (:217)
+ *   z'      = z with z'_a replaced by the constant 0 (`ones` at :208 is zeros_like)            (:206-209)
+ *   y       = first best open-set channel (k >= C) if its logit is > 0, else class 0           (:220-222)
+ *   unknown = -log softmax(z')_y                                                               (:229)
+ *   loss    = mean_valid(known) + lambda_place * mean_valid(unknown)                           (:230)
+ *   logits [B, CK, h, w] f32 LOW-res; C = num_classes, CK = num_classes + open_classes
+ *   dlogits_raw [B, CK, h, w]: SUM over valid pixels of dLoss_pixel/dlogits (not yet divided by the count)
+ *   stats f64[2]: {loss sum, valid count}; loss_mean f32 (NaN when no pixel is valid, like the reference)
+ *   finish with simt_head_scale(dlogits_raw, n, stats, 0, 0, grad_out, NULL).
+ *   workspace: simt_head_workspace_bytes(...) bytes, zero-filled once (shared with the head calls).
+ * ------------------------------------------------------------------------- */
+int simt_placeholder_fwdbwd(const float* logits, int B, int CK, int h, int w, int C, int H, int W,
+                            float thres, float lambda_place, float* dlogits_raw, double* stats,
+                            float* loss_mean, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Inner W optimisation (tools/trainV2_simt.py:326-339), one head, ONE single-CTA launch.
  * Runs n_steps rounds of: W = softmax(weight with diag := -1e4, dim 1) - I
  * (model/deeplab_multi.py:277-286), loss = sum((W T)^2) (:336), backward (:337), and a

@@ -84,6 +84,57 @@ def close(x, y, what, tol):
     assert err <= tol * max(ref, 1e-30), f"{what}: restatement differs from the reference ({err:.3e} vs norm {ref:.3e})"
 
 
+def _reference_placeholder_loss():
+    """The reference's own ``Placeholder_loss`` (tools/trainV2_simt.py:202-230), compiled from its source file.
+    The script cannot be imported (it parses the command line and pulls in datasets / matplotlib at import
+    time), so the one FunctionDef is taken out of the file with ``ast`` and executed unmodified."""
+    import ast
+    import types
+    path = os.path.join(REF, "tools", "trainV2_simt.py")
+    tree = ast.parse(open(path).read(), path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "Placeholder_loss")
+    ns = {"torch": torch, "args": types.SimpleNamespace(num_classes=19, open_classes=0, lambda_Place=0.1)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["Placeholder_loss"], ns["args"]
+
+
+def gen_placeholder(O, manifest):
+    import torch.nn as nn
+    ref_fn, args = _reference_placeholder_loss()
+    cases = [  # name, B, K, h, w, H, W, thres, logit scale
+        ("place_K4", 2, 4, 9, 17, 64, 128, 0.8, 3.0),
+        ("place_K15", 1, 15, 5, 9, 33, 65, 0.8, 4.0),
+        ("place_K4_nothres", 1, 4, 7, 6, 41, 29, None, 2.0),
+    ]
+    for name, B, K, h, w, H, W, thres, sc in cases:
+        CK = 19 + K
+        args.num_classes, args.open_classes, args.lambda_Place = 19, K, 0.1           # :63 default
+        g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 10007)
+        lo = sc * torch.randn(B, CK, h, w, generator=g)
+        # make a good share of pixels confidently known-class, some confidently open-set, some below the threshold
+        boost = torch.randint(0, CK, (B, 1, h, w), generator=g)
+        lo = lo + 6.0 * torch.nn.functional.one_hot(boost[:, 0], CK).permute(0, 3, 1, 2) * \
+            (torch.rand(B, 1, h, w, generator=g) < 0.7)
+        interp = nn.Upsample(size=(H, W), mode="bilinear", align_corners=True)           # :301
+        out = {"logits": lo.numpy(), "size": np.array([H, W]), "thres": np.float64(-1.0 if thres is None else thres),
+               "lambda_place": np.float64(0.1), "K": np.int64(K)}
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            lg = lo.to(dt).clone().requires_grad_(True)
+            loss = ref_fn(interp(lg), 19, K, thres=thres)                                # :371,398
+            loss.backward()
+            l_o, g_o = O.placeholder_fwd_bwd(lo, (H, W), 19, K, thres, 0.1, dt)
+            close(l_o, loss.detach(), name + " loss", tol=1e-6)
+            close(g_o, lg.grad, name + " grad", tol=1e-6)
+            out[f"loss_{tag}"] = loss.detach().numpy()
+            out[f"dlogits_{tag}"] = lg.grad.numpy()
+        up = interp(lo)
+        am = up.argmax(1)
+        out["n_valid"] = np.int64(((am < 19) & ((torch.softmax(up, 1).max(1)[0] > thres) if thres is not None
+                                                else torch.ones_like(am, dtype=torch.bool))).sum())
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        manifest["cases"].append(name)
+
+
 def gen_wfit(sig_NTM, sig_W, O, manifest):
     # ---- inner W optimisation (a8), trainV2_simt.py:271-280,317-339 with the reference's modules + torch Adam ----
     for K in (4, 15):
@@ -138,12 +189,13 @@ def main():
     from oracle import simt_oracle as O
 
     manifest = {"torch": torch.__version__, "numpy": np.__version__, "cases": []}
-    if sys.argv[1:] == ["--only", "wfit"]:      # add / refresh the wfit cases without touching the other fixtures
+    if len(sys.argv) == 3 and sys.argv[1] == "--only":   # add / refresh one family without touching the other fixtures
+        fam = sys.argv[2]
         manifest = json.load(open(os.path.join(OUT, "MANIFEST.json")))
-        manifest["cases"] = [c for c in manifest["cases"] if not c.startswith("wfit_")]
-        gen_wfit(sig_NTM, sig_W, O, manifest)
+        manifest["cases"] = [c for c in manifest["cases"] if not c.startswith(fam + "_")]
+        {"wfit": lambda: gen_wfit(sig_NTM, sig_W, O, manifest), "place": lambda: gen_placeholder(O, manifest)}[fam]()
         json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
-        print("wrote wfit cases;", len(manifest["cases"]), "golden cases in", OUT)
+        print("wrote", fam, "cases;", len(manifest["cases"]), "golden cases in", OUT)
         return
     class_dist = np.load(os.path.join(REF, "ClassDist", "ClassDist_bapa.npy"))
     np.save(os.path.join(OUT, "ClassDist_bapa.npy"), class_dist)
@@ -260,6 +312,7 @@ def main():
         manifest["cases"].append(f"reg_K{K}")
 
     gen_wfit(sig_NTM, sig_W, O, manifest)
+    gen_placeholder(O, manifest)
 
     # ---- pseudo labels + class-posterior relabel (section 8(f) row 2), executed from trainV2_simt.py:354-365,387-393 ----
     import torch.nn as nn

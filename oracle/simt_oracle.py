@@ -297,13 +297,51 @@ def eval_two_scale_argmax(out2_a: torch.Tensor, out2_b, out_size, num_classes: i
     return np.stack(outs).astype(np.uint8)
 
 
+def placeholder_loss(pred, num_classes, open_classes, thres=None, lambda_place=0.1):
+    """``Placeholder_loss`` of tools/trainV2_simt.py:202-230 on the UPSAMPLED logits ``pred`` [B, C+K, H, W].
+
+    Restated per pixel (a = arg-max channel, first on ties):
+      * known-class term (:205,212-217): CE(pred, a) on pixels with a < C (and max softmax prob > thres);
+      * ``predict`` (:206-209): pred with the arg-max channel replaced by the CONSTANT -0.0 -- ``ones`` at :208 is
+        ``zeros_like``, so ``-1000. * ones`` is zero, not -1000 (the reference's quirk, kept);
+      * open-set target (:220-223): arg-max over [0]*C ++ predict[C:], i.e. the first best open-set channel when its
+        logit is > 0 and class 0 otherwise; 255 wherever the known-class label is 255;
+      * unknown term (:229): CE(predict, target); result = known + lambda_place * unknown (:230).
+    """
+    ck = num_classes + open_classes
+    pseudo = torch.argmax(pred, dim=1)                                                    # :205
+    onehot = F.one_hot(pseudo, ck).permute(0, 3, 1, 2).to(pred.dtype)                     # :206
+    predict = torch.where(onehot > 0, torch.zeros_like(pred), pred)                       # :207-209 (-1000 * 0)
+    ones = torch.ones_like(pseudo)
+    pseudo1 = torch.where(pseudo < num_classes, pseudo, 255 * ones)                       # :213
+    if thres is not None:
+        pred_max = torch.softmax(pred.detach(), dim=1).max(1)[0]                          # :215
+        pseudo1 = torch.where(pred_max > thres, pseudo1, 255 * ones)                      # :216
+    loss_known = F.cross_entropy(pred, pseudo1, ignore_index=IGNORE_LABEL)                # :217
+    predict_open = torch.zeros_like(predict)                                              # :220
+    predict_open[:, num_classes:] = predict[:, num_classes:].detach()                     # :221
+    y = torch.argmax(predict_open, dim=1)                                                 # :222
+    y = torch.where(pseudo1 == 255, 255 * ones, y)                                        # :223
+    loss_unknown = F.cross_entropy(predict, y, ignore_index=IGNORE_LABEL)                 # :229
+    return loss_known + lambda_place * loss_unknown                                       # :230
+
+
+def placeholder_fwd_bwd(logits_lo, out_size, num_classes, open_classes, thres=None, lambda_place=0.1,
+                        dtype=torch.float32):
+    """(loss, dLoss/dlogits_lo) of upsample (:371-372) -> Placeholder_loss (:398-399), via autograd."""
+    lg = logits_lo.detach().to(dtype).clone().requires_grad_(True)
+    loss = placeholder_loss(upsample_bilinear_ac(lg, out_size), num_classes, open_classes, thres, lambda_place)
+    loss.backward()
+    return loss.detach(), lg.grad.detach()
+
+
 def training_step_loss(pred1_lo, pred2_lo, fixed_out2_lo, label_target, T1, T2, W1, W2, out_size, num_classes,
                        lambda_seg=0.1, lambda_convex=0.1, lambda_volume=1.0, lambda_anchor=1.0,
-                       thres_high=0.8, thres_low=0.2):
-    """The head part of one training iteration, tools/trainV2_simt.py:351-424, WITHOUT the backbone and
-    without Placeholder_loss (section 8(f) row 4, not built): pseudo labels (:351-365), upsample (:371-372), anchor
-    (:375-384), class-posterior relabel + seg_loss (:387-395), T-corrected losses (:402-409), convex / volume
-    (:412-421), combination (:423-424) with the published weights of sh_simt.sh:16.  B must be 1 (anchor)."""
+                       thres_high=0.8, thres_low=0.2, lambda_place=None):
+    """The head part of one training iteration, tools/trainV2_simt.py:351-424, WITHOUT the backbone: pseudo labels
+    (:351-365), upsample (:371-372), anchor (:375-384), class-posterior relabel + seg_loss (:387-395),
+    Placeholder_loss (:398-399, only when ``lambda_place`` is given), T-corrected losses (:402-409), convex /
+    volume (:412-421), combination (:423-424) with the published weights of sh_simt.sh:16.  B must be 1 (anchor)."""
     up = lambda x: upsample_bilinear_ac(x, out_size)
     labelC_flat = label_c_flat(fixed_out2_lo, out_size)
     pred1, pred2 = up(pred1_lo), up(pred2_lo)                                                  # :371-372
@@ -316,7 +354,12 @@ def training_step_loss(pred1_lo, pred2_lo, fixed_out2_lo, label_target, T1, T2, 
     convex = convex_loss([W1, W2], [T1, T2])                                                   # :412-415
     volume = volume_loss([T1, T2])                                                             # :417-421
     loss_target = loss_p2 + loss_y2 + lambda_seg * loss_p1 + lambda_seg * loss_y1             # :423
-    return loss_target + lambda_convex * convex + lambda_volume * volume + lambda_anchor * anchor   # :424
+    place = 0.0
+    if lambda_place is not None:
+        open_classes = pred1_lo.shape[1] - num_classes
+        place = lambda_seg * placeholder_loss(pred1, num_classes, open_classes, thres_high, lambda_place)   # :398
+        place = place + placeholder_loss(pred2, num_classes, open_classes, thres_high, lambda_place)        # :399
+    return place + loss_target + lambda_convex * convex + lambda_volume * volume + lambda_anchor * anchor   # :424
 
 
 # --------------------------------------------------------------------------

@@ -38,6 +38,8 @@ SIGNATURES = {
     "simt_label_map": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
     "simt_hist_set_tuning": (None, [c_int, c_int, c_int]),
     "simt_t_regularizers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "simt_placeholder_fwdbwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "simt_w_fit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_double, c_double,
                            c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "simt_anchor_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -44,7 +44,7 @@
 
 namespace simt {
 
-enum { MODE_FWD = 0, MODE_FWDBWD = 1, MODE_BWD = 2 };
+enum { MODE_FWD = 0, MODE_FWDBWD = 1, MODE_BWD = 2, MODE_PLACE = 3 };
 
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr double kLn2 = 0.6931471805599453094;
@@ -68,6 +68,7 @@ struct HeadArgs {
   long long* part_cnt;  // [grid]
   int* err;
   int label_words_ok;  // uint8 labels: buffer 4-byte aligned and a multiple of 4 bytes long
+  float place_thres, place_lambda;  // MODE_PLACE: confidence threshold (< 0: none), weight of the open-set term
 };
 
 // ---- pixel <-> cell mapping, identical float arithmetic on host and device ----------
@@ -123,6 +124,13 @@ template <int LPR>
 __device__ __forceinline__ float group_max(float v, unsigned gmask) {
   if (LPR >= 2) v = fmaxf(v, __shfl_xor_sync(gmask, v, 1));
   if (LPR >= 4) v = fmaxf(v, __shfl_xor_sync(gmask, v, 2));
+  return v;
+}
+
+template <int LPR>
+__device__ __forceinline__ int group_min_i(int v) {
+  if (LPR >= 2) v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  if (LPR >= 4) v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
 
@@ -243,6 +251,7 @@ template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   static_assert(CPL % 2 == 0, "channels per lane are processed as fp32x2 pairs");
   constexpr bool BWD = (MODE != MODE_FWD);
+  constexpr bool PLACE = (MODE == MODE_PLACE);   // Placeholder_loss: labels are derived from the logits, no T
   constexpr int NP = CPL / 2;    // channel pairs per lane
   constexpr int CKP = CPL * LPR;
   constexpr int CPW = 32 / LPR;  // cells per warp unit
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   float* Ew = Esm + (size_t)(tid >> 5) * kEdgeRows * (CKP + 1);
 
   // ---- one-time per CTA: -T transposed ([y][k], zero padded), pixel/cell tables ----
-  for (int i = tid; i < C * CKP; i += NT) {
+  for (int i = tid; i < (PLACE ? 0 : C * CKP); i += NT) {
     int y = i / CKP, k = i - y * CKP;
     float v = 0.f;
     if (k < CK) v = A.T ? __ldg(A.T + (size_t)k * C + y) : (k == y ? 1.f : 0.f);
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     const int Yfirst = Yall0 + (int)(((long long)(Yall1 - Yall0) * part) / A.rs);
     const int Ylast = Yall0 + (int)(((long long)(Yall1 - Yall0) * (part + 1)) / A.rs);  // one past the last row
     RawRun raw_next = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u};
-    if (Yfirst < Ylast)
+    if (!PLACE && Yfirst < Ylast)
       raw_next = LabelFetch<LabelT>::issue(labels, ((long long)b * A.H + Yfirst) * A.W + xa, nrun, labels_end,
                                            A.label_words_ok != 0, A.ignore, C);
 
@@ -393,8 +402,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
       for (int Y = Y0; Y < Y1; ++Y) {
         const float ly = lambda_of(Y, A.sy, cy);
         const long long rowbase = ((long long)b * A.H + Y) * A.W + xa;
-        const unsigned long long codes = LabelFetch<LabelT>::finish(raw_next, nrun);
-        if (Y + 1 < Ylast)  // next row's labels are in flight during this row's arithmetic
+        const unsigned long long codes = PLACE ? 0ULL : LabelFetch<LabelT>::finish(raw_next, nrun);
+        if (!PLACE && Y + 1 < Ylast)  // next row's labels are in flight during this row's arithmetic
           raw_next = LabelFetch<LabelT>::issue(labels, rowbase + A.W, nrun, labels_end, A.label_words_ok != 0,
                                                A.ignore, C);
         float2 Gs[NP], G1[NP];
@@ -424,6 +433,79 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #pragma unroll
           for (int q = 0; q < NP; ++q) a[q] = fadd2(a[q], nM);
 
+          if constexpr (PLACE) {
+            // ---- Placeholder_loss (tools/trainV2_simt.py:202-230) on this row's pixels --------------------
+            // Per pixel: a = arg-max channel (first on ties); valid iff a < C and max prob > thres;
+            //   known   = -log softmax(z)_a
+            //   unknown = CE(z', y) with z' = z except z'_a = 0 (a CONSTANT: `ones` at :208 is zeros_like), and
+            //             y = the first best open-set channel if its logit is > 0, else class 0 (:220-222)
+            // Both softmaxes are taken relative to their own exact maximum (no range assumptions).
+            const float tz = -M;  // the logit 0 in this row's shifted log2 domain
+            auto pixel = [&](const float lam, const bool wv) {
+              float t[CPL], e[CPL], f[CPL];
+              const float2 L = bcast2(lam);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) {
+                const float2 tt = ffma2(L, d[q], a[q]);
+                t[2 * q] = tt.x; t[2 * q + 1] = tt.y;
+              }
+              float m0 = -INFINITY, mo = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) {
+                m0 = fmaxf(m0, t[j]);
+                mo = fmaxf(mo, (kbase + j >= C) ? t[j] : -INFINITY);
+              }
+              m0 = group_max<LPR>(m0, 0xffffffffu);
+              mo = group_max<LPR>(mo, 0xffffffffu);
+              int ia = 1 << 20, io = 1 << 20;
+#pragma unroll
+              for (int j = CPL - 1; j >= 0; --j) {
+                if (t[j] == m0) ia = kbase + j;
+                if (kbase + j >= C && t[j] == mo) io = kbase + j;
+              }
+              ia = group_min_i<LPR>(ia);
+              io = group_min_i<LPR>(io);
+              float m2 = -INFINITY;  // best channel other than the arg-max: the maximum of z' is max(m2, 0)
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) m2 = fmaxf(m2, (kbase + j == ia) ? -INFINITY : t[j]);
+              m2 = group_max<LPR>(m2, 0xffffffffu);
+              const float ms = fmaxf(m2, tz);
+              float su = 0.f, sp = 0.f;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) {
+                e[j] = ex2_approx(t[j] - m0);
+                f[j] = (kbase + j == ia) ? 0.f : ex2_approx(t[j] - ms);
+                su += e[j];
+                sp += f[j];
+              }
+              su = group_sum<LPR>(su, 0xffffffffu);                          // >= 1; max prob = 1 / su
+              sp = group_sum<LPR>(sp, 0xffffffffu) + ex2_approx(tz - ms);    // >= 1
+              const bool valid = wv && ia < C && (1.f > A.place_thres * su);
+              const bool open_pos = mo > tz;                                  // an open-set logit > 0
+              const int y = open_pos ? io : 0;
+              const float t_first = __shfl_sync(0xffffffffu, t[0], lane & ~(LPR - 1));  // channel 0 of this pixel
+              const float ty = (y == ia) ? tz : (open_pos ? mo : t_first);   // z'_y in the shifted domain
+              if (valid) {
+                loss_acc -= lg2_approx(su) + A.place_lambda * (lg2_approx(sp) + (ms - ty));
+                cnt += 1;
+              }
+              const float r = valid ? rcp_approx(su * sp) : 0.f;
+              const float rs = r * sp, rp = A.place_lambda * (r * su);
+              const float oa = valid ? 1.f : 0.f, oy = (valid && y != ia) ? A.place_lambda : 0.f;
+#pragma unroll
+              for (int j = 0; j < CPL; ++j) {
+                float g = fmaf(f[j], rp, e[j] * rs);
+                g -= (kbase + j == ia) ? oa : 0.f;
+                g -= (kbase + j == y) ? oy : 0.f;
+                if (j & 1) { Gs[j >> 1].y += g; G1[j >> 1].y = fmaf(lam, g, G1[j >> 1].y); }
+                else       { Gs[j >> 1].x += g; G1[j >> 1].x = fmaf(lam, g, G1[j >> 1].x); }
+              }
+            };
+            for (int p = 0; p < nmax; p += 2) {  // warp-uniform: lanes past their run execute predicated-off pixels
+              pixel(lambda_of(xa + p, A.sx, cx), p < nrun);
+              pixel(lambda_of(xa + p + 1, A.sx, cx), p + 1 < nrun);
+            }
+          } else {
           // One step = two pixels of every lane's run (two independent MUFU/FMA chains per lane,
           // channel pairs packed into fp32x2 instructions).  WARP-UNIFORM: lane groups exchange partial
           // sums with full-mask shuffles, so invalid lanes/pixels are predicated off (w0/w1), never
@@ -559,6 +641,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           };
           if (__all_sync(0xffffffffu, range_safe)) run_row(std::false_type{});
           else run_row(std::true_type{});
+          }  // !PLACE
         }
         if (BWD) {
           // node column cx of this row = G0(cx) + G1(cx-1); the left neighbour is LPR lanes below
@@ -641,7 +724,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   }
 
   // ---- CTA epilogue: partials ---------------------------------------------------------------
-  if (BWD && cur >= 0) flush_lane();
+  if (BWD && !PLACE && cur >= 0) flush_lane();
   if (badf) atomicOr(A.err, SIMT_ERRBIT_LABEL_RANGE);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -677,7 +760,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
   if ((int)blockIdx.x < (int)gridDim.x - 1) {
     const int o = blockIdx.x * 32 + tx;  // output index in the [y][k] layout of the tiles
     double s = 0.0;
-    if (o < ndt && mode != MODE_FWD) {
+    if (o < ndt && (mode == MODE_FWDBWD || mode == MODE_BWD)) {
       float v[kFinMaxPer];
 #pragma unroll
       for (int q = 0; q < kFinMaxPer; ++q) {
@@ -818,6 +901,7 @@ static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid
 }
 
 static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
+  if (mode == MODE_PLACE) return dispatch<MODE_PLACE, uint8_t>(A, P, st, grid_out);
   if (label_bytes == 1) {
     if (mode == MODE_FWD) return dispatch<MODE_FWD, uint8_t>(A, P, st, grid_out);
     if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, uint8_t>(A, P, st, grid_out);
@@ -937,6 +1021,40 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   return (int)cudaGetLastError();
 }
 
+static int run_place(const float* logits, int B, int CK, int h, int w, int C, int H, int W, float thres, float lambda_place,
+                     float* dlogits, double* stats, float* loss_mean, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st) {
+  if (!logits || !dlogits || !workspace || (!stats && !loss_mean)) return SIMT_EINVAL;
+  if (B <= 0 || CK <= 0 || C <= 0 || C > CK || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SIMT_EINVAL;
+  if (CK > kMaxCKP || C > 254) return SIMT_EUNSUPPORTED;
+  if (workspace_bytes < simt_head_workspace_bytes(B, CK, C, h, w, H, W)) return SIMT_EWORKSPACE;
+  HeadArgs A{};
+  Plan P{};
+  A.logits = logits; A.T = nullptr; A.labels = nullptr;
+  A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = 255;
+  A.gscale = 1.f; A.dlogits = dlogits; A.err = nullptr;
+  A.place_thres = thres; A.place_lambda = lambda_place;
+  int rc = make_plan(MODE_PLACE, B, CK, C, h, w, H, W, &A, &P);
+  if (rc) return rc;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  A.counter = reinterpret_cast<unsigned long long*>(ws);
+  A.part_loss = reinterpret_cast<double*>(ws + 64);
+  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
+  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
+  int grid = 0;
+  rc = dispatch_all(MODE_PLACE, 1, A, P, st, &grid);
+  if (rc) return rc;
+  // one block: loss / count partials and the scheduler re-arm (there are no dT tiles in this mode)
+  head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, MODE_PLACE, 1.f,
+                                           A.counter, stats, loss_mean, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace simt
 
 using namespace simt;
@@ -976,6 +1094,13 @@ int simt_head_bwd(const float* logits, int B, int CK, int h, int w, const float*
                   void* workspace, size_t workspace_bytes, void* stream) {
   return run_head(MODE_BWD, logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, scale, dlogits, nullptr,
                   nullptr, dT, err_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int simt_placeholder_fwdbwd(const float* logits, int B, int CK, int h, int w, int C, int H, int W, float thres,
+                            float lambda_place, float* dlogits_raw, double* stats, float* loss_mean, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return run_place(logits, B, CK, h, w, C, H, W, thres, lambda_place, dlogits_raw, stats, loss_mean, workspace,
+                   workspace_bytes, (cudaStream_t)stream);
 }
 
 int simt_head_scale(float* dlogits, long long n_dlogits, const double* stats, int CK, int C, const float* grad_out,

@@ -144,3 +144,31 @@ def test_inner_w_loop_matches_reference(K):
             assert _close(st[i]["m"].numpy(), g[f"m{i + 1}_after{outer}"], 1e-5)
             assert _close(st[i]["v"].numpy(), g[f"v{i + 1}_after{outer}"], 1e-5)
             assert _close(grads[i].numpy(), g[f"ntm_grad{i + 1}_outer{outer}"], 1e-5)
+
+
+@pytest.mark.parametrize("name", ["place_K4", "place_K15", "place_K4_nothres"])
+@pytest.mark.parametrize("tag,dtype", [("f32", torch.float32), ("f64", torch.float64)])
+def test_placeholder_loss_matches_reference(name, tag, dtype):
+    """Placeholder_loss (trainV2_simt.py:202-230) after the upsample of :371, against values recorded from the
+    reference's own function (compiled from its source, see oracle/make_golden.py)."""
+    g = load_golden(name)
+    thres = None if float(g["thres"]) < 0 else float(g["thres"])
+    loss, dl = O.placeholder_fwd_bwd(torch.from_numpy(g["logits"]), tuple(int(s) for s in g["size"]), 19, int(g["K"]),
+                                     thres, float(g["lambda_place"]), dtype)
+    assert _close(loss.numpy(), g[f"loss_{tag}"], 1e-6)
+    assert _close(dl.numpy(), g[f"dlogits_{tag}"], 1e-6)
+
+
+def test_placeholder_quirks():
+    """The constant that replaces the arg-max logit is 0 (``-1000. * zeros_like``), and the open-set target falls
+    back to class 0 when no open-set logit is positive."""
+    z = torch.tensor([2.0, 1.0, -3.0, -0.5, -0.25]).view(1, 5, 1, 1)     # C = 3 known, K = 2 open (both <= 0)
+    loss = O.placeholder_loss(z, 3, 2, None, 1.0)
+    known = torch.logsumexp(z.flatten(), 0) - 2.0
+    zp = z.flatten().clone(); zp[0] = 0.0
+    unknown = torch.logsumexp(zp, 0) - zp[0]                               # y = 0 -> the replaced (constant 0) logit
+    assert abs(float(loss) - float(known + unknown)) < 1e-6
+    z[0, 4] = 0.75                                                         # now an open-set logit is > 0 -> y = 4
+    loss = O.placeholder_loss(z, 3, 2, None, 1.0)
+    zp = z.flatten().clone(); zp[0] = 0.0
+    assert abs(float(loss) - float(known * 0 + torch.logsumexp(z.flatten(), 0) - 2.0 + torch.logsumexp(zp, 0) - 0.75)) < 1e-6

@@ -1,4 +1,4 @@
-"""GPU: one whole training iteration of the head (tools/trainV2_simt.py:351-424 minus the backbone and
+"""GPU: one whole training iteration of the head (tools/trainV2_simt.py:351-424 minus the backbone, with
 Placeholder_loss) through the simt_b200 API against the CPU oracle's restatement of the same lines:
 total loss and every gradient that leaves the head (both heads' low-res logits, both NTM parameters, both
 W parameters)."""
@@ -35,12 +35,16 @@ def test_training_iteration_head_matches_reference_lines(K):
     pred1 = 2.0 * torch.randn(1, CK, h, w, generator=g)
     pred2 = 2.0 * torch.randn(1, CK, h, w, generator=g)
     out2 = 2.0 * torch.randn(1, 19, h, w, generator=g)
+    for p in (pred1, pred2):   # confident nodes, so that Placeholder_loss's 0.8 threshold keeps a share of the pixels
+        p += 5.0 * torch.nn.functional.one_hot(torch.randint(0, CK, (1, h, w), generator=g), CK).permute(0, 3, 1, 2) * \
+            (torch.rand(1, 1, h, w, generator=g) < 0.6)
     _, labels = O.synth_head_inputs(1, CK, h, w, H, W, seed=3, coherent=True, block=(20, 28), class_dist=class_dist())
 
     # ---- oracle (CPU, fp64 for a clean comparison) ----
     ntm1, ntm2, w1, w2 = [m.double() for m in _make(K, 7)]
     p1o, p2o = pred1.double().requires_grad_(True), pred2.double().requires_grad_(True)
-    ref = O.training_step_loss(p1o, p2o, out2.double(), labels.long(), ntm1(), ntm2(), w1(), w2(), (H, W), 19)
+    ref = O.training_step_loss(p1o, p2o, out2.double(), labels.long(), ntm1(), ntm2(), w1(), w2(), (H, W), 19,
+                               lambda_place=0.1)
     ref.backward()
 
     # ---- product (GPU) ----
@@ -56,7 +60,9 @@ def test_training_iteration_head_matches_reference_lines(K):
     c1, vol1 = simt_b200.t_regularizers(T1, W1)                                          # :412-421
     c2, vol2 = simt_b200.t_regularizers(T2, W2)
     anchor = simt_b200.anchor_loss([p1, p2], [T1, T2], out2.to(dev), (H, W))             # :375-384
-    total = (loss_p2 + loss_y2 + 0.1 * loss_p1 + 0.1 * loss_y1) + 0.1 * (c1 + c2) + 1.0 * (vol1 + vol2) + 1.0 * anchor
+    place = 0.1 * simt_b200.Placeholder_loss(p1, 19, K, 0.8, out_size=(H, W), lambda_place=0.1)   # :398
+    place = place + simt_b200.Placeholder_loss(p2, 19, K, 0.8, out_size=(H, W), lambda_place=0.1)  # :399
+    total = place + (loss_p2 + loss_y2 + 0.1 * loss_p1 + 0.1 * loss_y1) + 0.1 * (c1 + c2) + 1.0 * (vol1 + vol2) + 1.0 * anchor
     total.backward()
     simt_b200.check_errors()
 
