@@ -165,6 +165,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return r;
 }
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+// fire-and-forget 8-byte vector reduction (sm_90+): *(float2*)p += v, p 8-byte aligned
+__device__ __forceinline__ void red_add_v2(float* p, float2 v) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 
 static constexpr float kPadLogit = -1.0e30f;  // padded channels: exp2 -> 0, no inf/NaN arithmetic
 
@@ -316,13 +320,14 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   // Hand the lane's dT accumulators (column `cur`) to the CTA tile: native red.global.add.f32, fire and
   // forget (shared-memory float atomics are CAS loops on sm_100 and need warp-collective workarounds).
   auto flush_lane = [&]() {
+    // (padded channels carry exact zeros and the tile has CKP columns, so pairs go out unguarded: one
+    // 8-byte red.global.add.v2.f32 per channel pair)
+    float* dst = ct + cur * CKP + kbase;
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      const float v = (j & 1) ? D2[j >> 1].y : D2[j >> 1].x;
-      if (kbase + j < CK) atomicAdd(&ct[cur * CKP + kbase + j], v);
+    for (int q = 0; q < NP; ++q) {
+      red_add_v2(dst + 2 * q, D2[q]);
+      D2[q] = make_float2(0.f, 0.f);
     }
-#pragma unroll
-    for (int q = 0; q < NP; ++q) D2[q] = make_float2(0.f, 0.f);
   };
 
   long long unit = claim_get(claim_raw());
@@ -513,9 +518,11 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // pixel 0 belongs to the lane's current label column `cur`; pixel 1 too unless `c1x >= 0`, in which
           // case the pair straddles a label boundary and pixel 1 uses column c1x (its T column is read from
           // shared memory where needed -- predicated loads, no extra live registers, no split step)
-          auto body = [&](auto check_underflow, const float lam0, const float lam1, const bool w0, const bool w1,
-                          const int c1x) {
-            const bool strad = c1x >= 0;
+          auto body = [&](auto check_underflow, auto may_straddle, const float lam0, const float lam1, const bool w0,
+                          const bool w1, const int c1x) {
+            // the straddle operands (predicated T-column loads + register copies) exist only in the instantiation
+            // that is entered when some lane of the warp has a label boundary inside its pair
+            const bool strad = decltype(may_straddle)::value && c1x >= 0;
             const float2* T1 = reinterpret_cast<const float2*>(Ts + (strad ? c1x : 0) * CKP + kbase);
             const float2 L0 = bcast2(lam0), L1 = bcast2(lam1);
             float2 e0[NP], e1[NP];
@@ -635,7 +642,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
                 switch_column(lab);
               }
               const int c1x = (v0 & v1 & (c0 != c1)) ? (int)c1 : -1;   // label boundary inside the pair
-              body(check_underflow, lambda_of(xa + p0, A.sx, cx), lambda_of(xa + p1, A.sx, cx), v0, v1, c1x);
+              const float lam0 = lambda_of(xa + p0, A.sx, cx), lam1 = lambda_of(xa + p1, A.sx, cx);
+              if (__any_sync(0xffffffffu, c1x >= 0)) body(check_underflow, std::true_type{}, lam0, lam1, v0, v1, c1x);
+              else body(check_underflow, std::false_type{}, lam0, lam1, v0, v1, c1x);
               done += 2;
             }
           };
