@@ -9,13 +9,15 @@ GPU, logits 19x65x129 -> 512x1024, C = 19 T-corrected CE, forward + backward):
     memset(dLogits) -> fused fwd/bwd kernel -> finalize -> [all-reduce of the 2.9 KB stats buffer
     when N > 1] -> scale kernel (dLogits, dT *= 1 / N_valid).
 `value`  : inputs already resident in HBM (rotating input sets larger than L2), timed with CUDA
-           events, barrier + synchronize on both sides, max over ranks.
+           events, barrier + synchronize on both sides, max over ranks.  At N = 1 every step is one
+           CUDA-graph replay (HeadRunner.graph_step); sharded runs launch eagerly around the all-reduce.
 `e2e`    : the same metric through the public API (simt_b200.HeadRunner.step fed by
            simt_b200.HostPrefetcher) with HOST inputs: per step a pinned-host -> device copy of logits
            and labels (double-buffered, overlapping the previous step's kernels) and a device -> host
            read of the loss are inside the timed region.
 `roofline`: algorithmic HBM bytes of the fused kernel / its mean launch duration, measured with
-           CUDA events recorded around that kernel on its stream during the timed steps.
+           CUDA events recorded around that kernel on its stream while the timed steps are re-run
+           eagerly right after the timed region (events inside a replayed graph cannot be read back).
 `cpu_baseline` / `--impl reference`: the reference's own CPU PyTorch path (oracle port of
            tools/trainV2_simt.py:371-372,402-409 + utils/loss.py, see oracle/simt_oracle.py)
            timed on this box's host cores.
@@ -302,9 +304,13 @@ def run_ours(args, rank, local_rank, world):
     # one output buffer set per input set so the dLogits writes also rotate through > L2
     runners = [simt_b200.HeadRunner(B_PER_GPU, CK, C, h, w, H, W, device=dev, group=group) for _ in range(n_sets)]
 
-    def step(i):
+    def step(i):                              # eager: memset + kernel + finalize [+ all-reduce] + scale
         lg, lab = sets[i % n_sets]
         return runners[i % n_sets].step(lg, T, lab)
+
+    def gstep(i):                             # the same step replayed from its CUDA graph (eager when sharded)
+        lg, lab = sets[i % n_sets]
+        return runners[i % n_sets].graph_step(lg, T, lab)
 
     def barrier():
         if world > 1:
@@ -315,20 +321,30 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         sampler.start()
 
-    lib.simt_b200_profile_enable(1)          # warm-up also creates the profiler's event pool
-    for i in range(max(args.warmup, 3)):
+    lib.simt_b200_profile_enable(1)          # eager warm-up also creates the profiler's event pool
+    for i in range(3):
         step(i)
     barrier()
-    lib.simt_b200_profile_read(None, None)   # reset the launch counter; the timed region reuses the events
+    lib.simt_b200_profile_enable(0)
+    for i in range(max(args.warmup, 3, n_sets if world == 1 else 0)):   # N=1: every buffer set captures its graph here
+        gstep(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     labeled = 0
     for i in range(args.steps):
-        step(i)
+        gstep(i)
         labeled += labeled_per_set[i % n_sets]
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # the dominant kernel's own duration: the same steps again, launched eagerly with the library's CUDA-event
+    # profiler around head_kernel on its stream (event pairs inside a replayed graph cannot be read back)
+    lib.simt_b200_profile_enable(1)
+    lib.simt_b200_profile_read(None, None)   # reset the launch counter
+    for i in range(args.steps):
+        step(i)
+    barrier()
     kms, klaunches = ctypes.c_double(), ctypes.c_longlong()
     lib.simt_b200_profile_read(ctypes.byref(kms), ctypes.byref(klaunches))
     lib.simt_b200_profile_enable(0)
@@ -409,9 +425,12 @@ def run_ours(args, rank, local_rank, world):
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
                     "api": "simt_b200.HeadRunner.step on inputs uploaded by simt_b200.HostPrefetcher from pinned host memory; loss read back every step"},
             "gpu_launches": 3 * args.steps,
+            "launch": ("one CUDA graph replay per step (memset, head_kernel, head_finalize_kernel, head_scale_kernel)"
+                       if world == 1 else "eager launches + one NCCL all-reduce per step"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "simt::head_kernel<CPL=10,LPR=2,FWDBWD,uint8>",
                          "kernel_ms": k_avg_ms, "launches_timed": int(klaunches.value),
+                         "kernel_timing": "CUDA events around head_kernel on its stream, the timed steps re-run eagerly right after the timed region",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch(B_PER_GPU), "peak_source": peak_src,
                          "note": "kernel is MUFU/FP32-issue bound, not HBM bound (DESIGN.md): 19 ex2 + 3 MUFU per pixel"},
             "clocks": sampler.summary(),

@@ -249,3 +249,28 @@ def test_full_size_invariants(B, K):
         assert float((dT_2 - dT).norm() / dT.norm()) <= 1e-5
         assert float((2 * dl_2[:B] - dl).norm() / dl.norm()) <= 1e-5
     simt_b200.check_errors()
+
+
+def test_headrunner_graph_step_matches_eager_and_sees_new_inputs():
+    """HeadRunner.graph_step (CUDA-graph replay of memset + kernel + finalize + scale) gives the eager result, and a
+    replay reads the CURRENT contents of the captured buffers."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    B, CK, h, w, H, W = 2, 19, 17, 33, 128, 256
+    sets = [O.synth_head_inputs(B, CK, h, w, H, W, seed=40 + i, coherent=True, ignore_frac=0.1) for i in range(2)]
+    T = O.sig_ntm_forward(torch.randn(CK, 19, generator=torch.Generator().manual_seed(2)), class_dist(), 19, 0).to(dev)
+    r = simt_b200.HeadRunner(B, CK, 19, h, w, H, W, device=dev)
+    lg, lab = sets[0][0].to(dev), sets[0][1].to(torch.uint8).to(dev)
+    for rep in range(3):                     # first call captures, the others replay
+        loss, dl, dT = r.graph_step(lg, T, lab)
+    ref = O.simt_head_fwd_bwd(sets[0][0], T.cpu(), sets[0][1], (H, W), torch.float64)
+    assert abs(float(loss) - float(ref[0])) <= TOL * abs(float(ref[0]))
+    assert rel_l2(dl.cpu().numpy(), ref[1].numpy()) <= TOL and rel_l2(dT.cpu().numpy(), ref[2].numpy()) <= TOL
+    lg.copy_(sets[1][0]); lab.copy_(sets[1][1].to(torch.uint8))          # refill in place -> same graph
+    loss, dl, dT = r.graph_step(lg, T, lab)
+    assert len(r._graphs) == 1
+    ref = O.simt_head_fwd_bwd(sets[1][0], T.cpu(), sets[1][1], (H, W), torch.float64)
+    assert abs(float(loss) - float(ref[0])) <= TOL * abs(float(ref[0]))
+    assert rel_l2(dl.cpu().numpy(), ref[1].numpy()) <= TOL and rel_l2(dT.cpu().numpy(), ref[2].numpy()) <= TOL
+    simt_b200.check_errors(dev)
