@@ -43,6 +43,7 @@ enum {
 
 #define SIMT_ERRBIT_LABEL_RANGE 1 /* head: label not ignore and not in [0, C)        */
 #define SIMT_ERRBIT_PRED_RANGE  2 /* histograms: n_cols*a+b outside [0, rows*cols)   */
+#define SIMT_ERRBIT_XCHG_TIMEOUT 4 /* sharded scale: a peer's stats never arrived       */
 
 int         simt_b200_abi_version(void);
 const char* simt_b200_strerror(int code);
@@ -181,6 +182,34 @@ int simt_anchor_stats(const float* logits, int B, int CK, int h, int w, int H, i
                       unsigned long long* scratch, void* stream);
 int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, int W,
                          const long long* pixel_idx, int n, float* rows, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Sharded step (one process per GPU, batch split over the ranks of ONE node): the all-reduce of
+ * `stats` fused into the scale kernel over peer memory (NVLink / NVSwitch P2P stores) instead of
+ * a library collective between finalize and scale.  The reference is single-process: its
+ * loss.backward() (tools/trainV2_simt.py:408-409,428) sees the whole batch, so the mean is over
+ * the GLOBAL valid-pixel count and dT is summed over ranks.
+ *
+ * simt_xchg_create: cudaMalloc + zero a mailbox of simt_xchg_bytes(2 + CK*C) bytes on the current
+ *   device and export its 64-byte CUDA IPC handle.  The caller exchanges the handles (any
+ *   transport: torch.distributed all-gather, MPI, a pipe) and opens every peer's mailbox with
+ *   simt_xchg_open (current device = the opener's GPU).  close / destroy undo open / create.
+ * simt_head_scale_sharded: replaces { all-reduce(stats); simt_head_scale } after simt_head_fwdbwd.
+ *   mailboxes: HOST array [world] of device pointers, mailboxes[rank] = this rank's own.
+ *   On return (stream order) stats holds the all-reduced values (same bits on every rank),
+ *   dlogits = raw * g / N_global, dT = sum_ranks raw dT * g / N_global, loss_mean the global mean.
+ *   Every rank must call it once per step, in the same order; world <= 8.  No host-side step
+ *   argument: the call sequence can be captured in a CUDA graph.  A peer that never arrives sets
+ *   SIMT_ERRBIT_XCHG_TIMEOUT in err_flag after a bounded wait instead of hanging.
+ * ------------------------------------------------------------------------- */
+size_t simt_xchg_bytes(int n_stats);
+int simt_xchg_create(size_t bytes, void** mailbox, unsigned char* handle64);
+int simt_xchg_open(const unsigned char* handle64, void** peer_mailbox);
+int simt_xchg_close(void* peer_mailbox);
+int simt_xchg_destroy(void* mailbox);
+int simt_head_scale_sharded(float* dlogits, long long n_dlogits, double* stats, int CK, int C,
+                            const float* grad_out, float* dT, float* loss_mean, int rank, int world,
+                            void* const* mailboxes, int* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Placeholder_loss (tools/trainV2_simt.py:202-230, called at :398-399 on the

@@ -38,6 +38,13 @@ SIGNATURES = {
     "simt_label_map": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
     "simt_hist_set_tuning": (None, [c_int, c_int, c_int]),
     "simt_t_regularizers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "simt_xchg_bytes": (c_size_t, [c_int]),
+    "simt_xchg_create": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_char_p]),
+    "simt_xchg_open": (c_int, [c_char_p, ctypes.POINTER(c_void_p)]),
+    "simt_xchg_close": (c_int, [c_void_p]),
+    "simt_xchg_destroy": (c_int, [c_void_p]),
+    "simt_head_scale_sharded": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "simt_placeholder_fwdbwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "simt_w_fit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_double, c_double,

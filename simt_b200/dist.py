@@ -6,10 +6,15 @@ collective; the only exchange per training step is ONE all-reduce(sum) of the 2 
 and ONE int64 all-reduce of the confusion matrix at the end of an evaluation.  dLogits stay local
 (they feed the local backbone replica).  Works with any torch.distributed backend: NCCL over
 NVLink on the GPU box, gloo in the CPU tests of this host logic.
+
+On one node the per-step exchange does not go through a library collective at all: ``PeerMailbox`` sets up CUDA-IPC
+mapped mailboxes between the ranks and the scale kernel exchanges the stats itself over NVLink peer stores
+(csrc/xchg.cu, ``simt_head_scale_sharded``); torch.distributed only carries the 64-byte handles once.
 """
 from __future__ import annotations
 
-from typing import Tuple
+import ctypes
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -48,3 +53,63 @@ def reduce_hist(hist: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return hist
+
+
+class PeerMailbox:
+    """CUDA-IPC mailboxes for the fused stats exchange of the sharded head (one per HeadRunner / buffer set).
+
+    Collective constructor: every rank of ``group`` (all on ONE node, <= 8) creates its mailbox, the 64-byte IPC
+    handles are all-gathered and every peer's mailbox is opened.  ``ptrs`` is the ctypes array
+    ``simt_head_scale_sharded`` takes.  Raises ``RuntimeError`` when peer mapping is not possible (other node, no
+    P2P); callers fall back to ``reduce_head_stats`` (a library all-reduce).
+    """
+
+    def __init__(self, n_stats: int, group=None, device: Optional[torch.device] = None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("PeerMailbox: at most 8 ranks (one node)")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.own = ctypes.c_void_p()
+        self.peers = {}
+        handle = ctypes.create_string_buffer(64)
+        ok, why = True, ""
+        with torch.cuda.device(self.dev):
+            rc = self.lib.simt_xchg_create(self.lib.simt_xchg_bytes(int(n_stats)), ctypes.byref(self.own), handle)
+            if rc:
+                ok, why = False, f"simt_xchg_create: code {rc}"
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (ok, bytes(handle.raw)), group=group)
+            ptrs = (ctypes.c_void_p * self.world)()
+            if ok and all(h[0] for h in handles):
+                for r, (_, hb) in enumerate(handles):
+                    if r == self.rank:
+                        ptrs[r] = self.own.value
+                        continue
+                    p = ctypes.c_void_p()
+                    rc = self.lib.simt_xchg_open(hb, ctypes.byref(p))
+                    if rc:
+                        ok, why = False, f"simt_xchg_open(rank {r}): code {rc}"
+                        break
+                    self.peers[r] = p
+                    ptrs[r] = p.value
+            else:
+                ok = False
+            # agree on the outcome: one rank failing means nobody uses the mailboxes
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            self.close()
+            raise RuntimeError("PeerMailbox: peer mapping unavailable" + (f" ({why})" if why else ""))
+        self.ptrs = ptrs
+
+    def close(self):
+        with torch.cuda.device(self.dev):
+            for p in self.peers.values():
+                self.lib.simt_xchg_close(p)
+            self.peers = {}
+            if self.own:
+                self.lib.simt_xchg_destroy(self.own)
+                self.own = ctypes.c_void_p()

@@ -60,6 +60,8 @@ def check_errors(dev=None) -> None:
             what.append("label outside [0, C) that is not the ignore label")
         if v & 2:
             what.append("n_cols*a+b outside the histogram table")
+        if v & 4:
+            what.append("sharded scale: a peer rank's stats never arrived (bounded wait expired)")
         raise IndexError("simt_b200: " + "; ".join(what))
 
 
@@ -203,7 +205,8 @@ class HeadRunner:
     ``graph_step`` is the same work replayed from a CUDA graph.
     """
 
-    def __init__(self, B, CK, C, h, w, H, W, device=None, ignore=255, label_dtype=torch.uint8, group=None):
+    def __init__(self, B, CK, C, h, w, H, W, device=None, ignore=255, label_dtype=torch.uint8, group=None,
+                 exchange="p2p"):
         self.lib = _lib.load()
         self.shape = (int(B), int(CK), int(C), int(h), int(w), int(H), int(W))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -221,6 +224,17 @@ class HeadRunner:
                    self.dlogits.data_ptr(), self.dT.data_ptr(), self.err.data_ptr())
         self._graphs = {}
         self._graph_keepalive = []
+        # sharded: the stats exchange is fused into the scale kernel over CUDA-IPC peer memory when every rank can
+        # map every other rank's mailbox (one node); otherwise one library all-reduce per step
+        self.mailbox = None
+        if group is not None and exchange == "p2p":
+            import torch.distributed as dist
+            if dist.get_world_size(group) > 1:
+                from .dist import PeerMailbox
+                try:
+                    self.mailbox = PeerMailbox(2 + CK * C, group, self.dev)
+                except RuntimeError:
+                    self.mailbox = None
 
     def fwdbwd(self, logits, T, labels, stream=None):
         B, CK, C, h, w, H, W = self.shape
@@ -240,9 +254,24 @@ class HeadRunner:
         if rc:
             _lib.check(rc, "simt_head_scale")
 
+    def scale_sharded(self, grad_out=None, stream=None):
+        """scale with the cross-rank stats exchange fused in (``simt_head_scale_sharded``); collective."""
+        B, CK, C, h, w, H, W = self.shape
+        _, _, stats, loss, dl, dT, err = self._p
+        mb = self.mailbox
+        rc = self.lib.simt_head_scale_sharded(dl, B * CK * h * w, stats, CK, C,
+                                              None if grad_out is None else grad_out.data_ptr(), dT, loss,
+                                              mb.rank, mb.world, mb.ptrs, err,
+                                              _stream_ptr() if stream is None else stream)
+        if rc:
+            _lib.check(rc, "simt_head_scale_sharded")
+
     def step(self, logits, T, labels, grad_out=None):
         stream = _stream_ptr()
         self.fwdbwd(logits, T, labels, stream)
+        if self.mailbox is not None:
+            self.scale_sharded(grad_out, stream)     # loss / stats / dT are global on return
+            return self.loss, self.dlogits, self.dT
         if self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
@@ -253,9 +282,10 @@ class HeadRunner:
         """``step`` replayed from a CUDA graph: memset + fused kernel + finalize + scale are captured ONCE for this exact
         set of buffers (keyed by their addresses) and re-launched as one graph afterwards -- the four launches of a
         step are launch-latency-bound next to a 90 us kernel.  The graph reads the buffers' CURRENT contents on every
-        replay (refill ``logits`` / ``labels`` / ``T`` in place).  Sharded runs (``group``) take the eager path: the
-        all-reduce stays outside any graph."""
-        if self.group is not None:
+        replay (refill ``logits`` / ``labels`` / ``T`` in place).  Sharded runs replay too when the stats exchange is
+        the fused peer-memory one (no library collective inside the graph); with the all-reduce fallback they take the
+        eager path."""
+        if self.group is not None and self.mailbox is None:
             return self.step(logits, T, labels, grad_out)
         key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
                None if grad_out is None else grad_out.data_ptr())

@@ -43,7 +43,21 @@ def _worker(rank, world, port, out_dir):
         meter = simt_b200.ConfusionMeter(19, mapping=O.CITYSCAPES_LABEL2TRAIN, device=dev)
         meter.update(gt, pr)
         sd.reduce_hist(meter.hist)
-        torch.save({"loss": loss.detach().cpu(), "dl": lg.grad.cpu(), "dT": Tt.grad.cpu(), "hist": meter.hist.cpu()},
+        # HeadRunner: the stats exchange fused into the scale kernel over CUDA-IPC peer memory (no NCCL in the step);
+        # five eager steps (both slot parities, slot reuse) and graph replays, each on a different global batch
+        runner = simt_b200.HeadRunner(3, 23, 19, 9, 17, 64, 128, device=dev, group=dist.group.WORLD)
+        lgb = torch.empty(3, 23, 9, 17, device=dev)
+        lbb = torch.empty(3, 64, 128, dtype=torch.uint8, device=dev)
+        p2p = []
+        Td = T.to(dev)
+        for it in range(8):
+            lg_i, lb_i = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=50 + it, coherent=True, block=(12, 20))
+            lgb.copy_(sd.shard_batch(lg_i, rank, world)); lbb.copy_(sd.shard_batch(lb_i, rank, world).to(torch.uint8))
+            l_i, dl_i, dT_i = (runner.step if it < 5 else runner.graph_step)(lgb, Td, lbb)
+            p2p.append((l_i.cpu().clone(), dl_i.cpu().clone(), dT_i.cpu().clone(), runner.stats.cpu().clone()))
+        simt_b200.check_errors(dev)
+        torch.save({"loss": loss.detach().cpu(), "dl": lg.grad.cpu(), "dT": Tt.grad.cpu(), "hist": meter.hist.cpu(),
+                    "p2p": p2p, "used_mailbox": runner.mailbox is not None, "n_graphs": len(runner._graphs)},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -73,3 +87,17 @@ def test_two_rank_head_equals_global_batch(tmp_path):
         gt, pr = O.synth_eval_pair(128, 256, seed=r, block=(24, 40))
         hist += O.fast_hist(O.label_mapping(gt, np.array(O.CITYSCAPES_LABEL2TRAIN)).flatten(), pr.flatten(), 19)
     assert np.array_equal(res[0]["hist"].numpy(), hist) and np.array_equal(res[1]["hist"].numpy(), hist)
+    # ---- fused peer-memory exchange (HeadRunner): every step equals the single-GPU answer on the global batch ----
+    assert res[0]["used_mailbox"] and res[1]["used_mailbox"], "CUDA-IPC peer mailboxes were not set up on a 2-GPU box"
+    assert res[0]["n_graphs"] == 1
+    for it in range(8):
+        lg_i, lb_i = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=50 + it, coherent=True, block=(12, 20))
+        lo, dlo, dTo = O.simt_head_fwd_bwd(lg_i, T, lb_i, (64, 128), torch.float64)
+        for r in range(world):
+            l_i, dl_i, dT_i, st_i = res[r]["p2p"][it]
+            assert abs(float(l_i) - float(lo)) <= 1e-5 * abs(float(lo)), (it, r)
+            assert float((dT_i.double() - dTo).norm() / dTo.norm()) <= 1e-5, (it, r)
+            a, b = sd.shard_range(6, r, world)
+            assert float((dl_i.double() - dlo[a:b]).norm() / dlo[a:b].norm()) <= 1e-5, (it, r)
+        # fixed rank-order sum: the all-reduced stats are bitwise identical on both ranks
+        assert torch.equal(res[0]["p2p"][it][3], res[1]["p2p"][it][3]), it
