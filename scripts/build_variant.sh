@@ -10,7 +10,7 @@ trap 'rm -f "$ROOT/simt_b200/csrc/_variant_$NAME.cu"' EXIT
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" \
      -c "$ROOT/simt_b200/csrc/_variant_$NAME.cu" -o "$ROOT/build/obj/head_$NAME.o"
 OBJS=""
-for f in capi hist nll2d reg wfit; do OBJS="$OBJS $ROOT/build/obj/$f.o"; done
+for f in "$ROOT"/simt_b200/csrc/*.cu; do b=$(basename "$f" .cu); case "$b" in head|_variant_*) ;; *) OBJS="$OBJS $ROOT/build/obj/$b.o";; esac; done
 nvcc -shared -o "$ROOT/variants/lib$NAME.so" "$ROOT/build/obj/head_$NAME.o" $OBJS \
      -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart static
 echo "$ROOT/variants/lib$NAME.so"
