@@ -15,8 +15,14 @@ static Profiler g_prof;
 
 bool prof_enabled() { return g_prof.on; }
 
+// events recorded into a capturing stream become graph nodes whose timestamps cannot be read back: skip them
+static bool capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+}
+
 void prof_begin(cudaStream_t st) {
-  if (!g_prof.on) return;
+  if (!g_prof.on || capturing(st)) return;
   if (g_prof.used == g_prof.starts.size()) {
     cudaEvent_t a, b;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -27,7 +33,7 @@ void prof_begin(cudaStream_t st) {
 }
 
 void prof_end(cudaStream_t st) {
-  if (!g_prof.on || g_prof.used >= g_prof.stops.size()) return;
+  if (!g_prof.on || g_prof.used >= g_prof.stops.size() || capturing(st)) return;
   cudaEventRecord(g_prof.stops[g_prof.used], st);
   ++g_prof.used;
 }

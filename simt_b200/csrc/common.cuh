@@ -40,6 +40,20 @@ inline int device_info(DeviceInfo* out) {
   return 0;
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory once per device (function attributes are per context, so a
+// process that drives several GPUs must set them on each).
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, bool (&done)[64], int bytes) {
+  int dev = 0;
+  SIMT_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return SIMT_EUNSUPPORTED;
+  if (!done[dev]) {
+    SIMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[dev] = true;
+  }
+  return 0;
+}
+
 // launch profiler (capi.cu)
 bool prof_enabled();
 void prof_begin(cudaStream_t st);

@@ -266,10 +266,10 @@ int simt_t_regularizers(const float* T, const float* W, int CK, int C, float* ou
   if (W && (!dT_convex || !dW_convex)) return SIMT_EINVAL;
   if (CK > kMaxC || C > kMaxC || C > CK) return SIMT_EUNSUPPORTED;
   const size_t smem = (size_t)(C * C + C * CK) * 8 + (size_t)(2 * CK * C + CK * CK) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMT_CUDA_TRY(cudaFuncSetAttribute(t_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+  static bool attr_done[64] = {};
+  {
+    const int rc = ensure_dynamic_smem(t_reg_kernel, attr_done, 160 * 1024);
+    if (rc) return rc;
   }
   t_reg_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(T, W, CK, C, out2, dT_convex, dT_volume, dW_convex);
   return (int)cudaGetLastError();

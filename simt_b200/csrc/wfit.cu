@@ -150,10 +150,10 @@ extern "C" int simt_w_fit(float* weight, float* exp_avg, float* exp_avg_sq, cons
   if (CK > kMaxW || C > kMaxW) return SIMT_EUNSUPPORTED;
   if (n_steps == 0) return 0;
   const size_t smem = (size_t)(5 * CK * CK + 3 * CK * C) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMT_CUDA_TRY(cudaFuncSetAttribute(w_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+  static bool attr_done[64] = {};
+  {
+    const int rc = ensure_dynamic_smem(w_fit_kernel, attr_done, 160 * 1024);
+    if (rc) return rc;
   }
   w_fit_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(weight, exp_avg, exp_avg_sq, T, CK, C, n_steps, step0, lr, beta1,
                                                        beta2, eps, dT_accum, losses);
