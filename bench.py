@@ -6,8 +6,8 @@
 
 A "step" is one pass of the hot path over one batch (BASELINE.json configs[1]: batch 8 per
 GPU, logits 19x65x129 -> 512x1024, C = 19 T-corrected CE, forward + backward):
-    memset(dLogits) -> fused fwd/bwd kernel -> finalize -> [all-reduce of the 2.9 KB stats buffer
-    when N > 1] -> scale kernel (dLogits, dT *= 1 / N_valid).
+    memset(dLogits) -> fused fwd/bwd kernel -> finalize -> scale kernel (dLogits, dT *= 1 / N_valid); when
+    N > 1 the scale kernel first exchanges the 2.9 KB stats buffer with its peers over CUDA-IPC peer memory.
 `value`  : inputs already resident in HBM (rotating input sets larger than L2), timed with CUDA
            events, barrier + synchronize on both sides, max over ranks.  At N = 1 every step is one
            CUDA-graph replay (HeadRunner.graph_step); sharded runs too, with the stats exchange fused into
@@ -439,6 +439,14 @@ def run_ours(args, rank, local_rank, world):
                          "note": "kernel is MUFU/FP32-issue bound, not HBM bound (DESIGN.md): 19 ex2 + 3 MUFU per pixel"},
             "clocks": sampler.summary(),
         }
+        # the pipe that bounds this kernel from below: 20 ex2 (19 channels + 1 pad) + 2 rcp + 1 lg2 lane-ops per pixel
+        # on the MUFU unit (16 lanes/clk/SM on B200), at the SM clock sampled under load
+        sm_mhz = out["clocks"].get("sm_mhz") or out["clocks"].get("sm_max_mhz") or 1965.0
+        mufu_ops = 23.0 * B_PER_GPU * H * W
+        mufu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6
+        out["roofline"]["compute"] = {"bound": "mufu", "achieved": mufu_ops / (k_avg_ms * 1e-3) / 1e9, "peak": mufu_peak / 1e9,
+                                      "unit": "G lane-ops/s", "frac": mufu_ops / (k_avg_ms * 1e-3) / mufu_peak,
+                                      "floor_ms": mufu_ops / mufu_peak * 1e3}
         if world == 1:
             out["cpu_baseline"] = run_cpu_baseline()
             out["eval_confusion"] = run_eval_confusion(lib, dev)
