@@ -20,9 +20,10 @@
 //   which gives identical values: for the last node lambda becomes exactly 1).
 //   unit       = UR cell-rows x CPW = 32/LPR cells, claimed dynamically by ONE WARP.
 //   lane group = LPR lanes own one cell; each lane owns CPL channels (CK <= CPL*LPR) and
-//                keeps the cell's 4 corner logits of its channels IN REGISTERS (pre-scaled
-//                by log2 e), so per pixel row the vertical lerp is 2 FFMA/channel and per
-//                pixel the horizontal lerp is ONE FFMA/channel:  t_k = a_k + lambda * d_k.
+//                stages the cell's 4 corner logits of its channels once per cell-row in a
+//                warp-private shared-memory slice (pre-scaled by log2 e, conflict-free), so per
+//                pixel row the vertical lerp is 2 FFMA2 per channel pair and per pixel the
+//                horizontal lerp is ONE FFMA2 per channel pair:  t_k = a_k + lambda * d_k.
 //   Softmax uses a per-row upper bound M of the logits instead of the per-pixel max (the
 //   interpolant is a convex combination of the row's end points); a pixel whose exp-sum
 //   underflows (only with > 2^40 dynamic range inside one cell) is redone with the exact max.
@@ -31,14 +32,15 @@
 //   the vertical transposed lerp is accumulated in registers too (Vt, Vb); per cell-row each
 //   lane group adds its two node rows to dLogits with red.global.add.f32 (coalesced across the
 //   warp); the unit's right edge column goes out the same way.
-//   dT: per-thread register accumulators D[] for the thread's current label column; flushed
-//   warp-collectively (shuffle tree, no atomics) into the warp's private fp64 shared tile
-//   when the label changes at a row boundary and at the end of every unit; a label change
-//   INSIDE a pixel run (rare on real label maps) takes a shared-memory atomic.
-//   Per-CTA partials (loss, count, dT; all fp64) are reduced in a fixed order by a small
-//   finalize kernel.  Units are claimed dynamically, so the grouping of the fp64 partial sums
-//   (and the order of the fp32 red.adds into dLogits, as in torch's own CUDA backward of
-//   upsample_bilinear2d) is not run-to-run deterministic in the last bit.
+//   dT: per-thread register accumulators D2[] for the thread's current label column, handed to the CTA's fp32 tile
+//   in global memory (L2 resident) with 8-byte red.global.add.v2.f32 whenever the lane's label changes and at the
+//   end of the CTA (shared-memory float atomics are CAS loops on sm_100 and collapse under contention).
+//   Per-CTA partials (loss and count in fp64, the dT tiles in fp32) are reduced in a fixed order by a small
+//   finalize kernel.  Units are claimed dynamically, so the grouping of the partial sums (and the order of the
+//   fp32 red.adds into dLogits, as in torch's own CUDA backward of upsample_bilinear2d) is not run-to-run
+//   deterministic in the last bit.
+//   MODE_PLACE reuses the same machinery for Placeholder_loss (tools/trainV2_simt.py:202-230): no labels, no T,
+//   the per-pixel body derives both label maps from the logits (see the body's comment).
 #include <type_traits>
 #include "common.cuh"
 
