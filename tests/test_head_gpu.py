@@ -274,3 +274,32 @@ def test_headrunner_graph_step_matches_eager_and_sees_new_inputs():
     assert abs(float(loss) - float(ref[0])) <= TOL * abs(float(ref[0]))
     assert rel_l2(dl.cpu().numpy(), ref[1].numpy()) <= TOL and rel_l2(dT.cpu().numpy(), ref[2].numpy()) <= TOL
     simt_b200.check_errors(dev)
+
+
+def test_host_prefetcher_double_buffering_delivers_every_batch():
+    """HostPrefetcher: pinned host batches arrive intact and in order while the previous step is still computing."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    B, CK, h, w, H, W = 2, 19, 9, 17, 64, 128
+    T = O.sig_ntm_forward(torch.randn(CK, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, 0)
+    host = []
+    for i in range(5):
+        lg, lab = O.synth_head_inputs(B, CK, h, w, H, W, seed=70 + i, coherent=True, ignore_frac=0.1)
+        host.append((lg.pin_memory(), lab.to(torch.uint8).pin_memory()))
+    pre = simt_b200.HostPrefetcher(B, CK, h, w, H, W, device=dev)
+    runner = simt_b200.HeadRunner(B, CK, 19, h, w, H, W, device=dev)
+    Td = T.to(dev)
+    losses = []
+    pre.submit(*host[0])
+    for i in range(5):
+        cur = pre.get()
+        if i + 1 < 5:
+            pre.submit(*host[i + 1])
+        loss, _, _ = runner.step(cur[0], Td, cur[1])
+        pre.release(cur)
+        losses.append(loss.clone())
+    torch.cuda.synchronize()
+    for i in range(5):
+        ref = O.simt_head_loss(host[i][0], T, host[i][1].long(), (H, W))
+        assert abs(float(losses[i]) - float(ref)) <= TOL * abs(float(ref)), i
