@@ -65,7 +65,8 @@ struct HeadArgs {
   float gscale;
   float* dlogits;
   unsigned long long* counter;  // dynamic unit scheduler (zero on entry; finalize re-zeroes it)
-  float* part_dT;       // [grid][C*CKP] per-CTA dT tiles (zero on entry; finalize re-zeroes them)
+  float* part_dT;       // [ntiles][C*CKP] per-SM dT tiles (zero on entry; finalize re-zeroes them)
+  int ntiles;           // = SM count: the CTAs resident on one SM share a tile (fewer tiles for finalize to reduce)
   double* part_loss;    // [grid]
   long long* part_cnt;  // [grid]
   int* err;
@@ -297,7 +298,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   }
   for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
   for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
-  float* ct = A.part_dT + (size_t)blockIdx.x * C * CKP;  // this CTA's dT tile in global memory (L2 resident)
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  float* ct = A.part_dT + (size_t)(smid % (unsigned)A.ntiles) * C * CKP;  // this SM's dT tile in global memory (L2 resident)
   __syncthreads();
 
   float2 D2[NP];     // dT accumulators (p_k / q) for the thread's current label column
@@ -758,11 +761,11 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 // (independent, many in flight), sums them in order, then re-zeroes the entries for the next call; the
 // 32 slice sums are added in order.  The last block reduces loss / count and re-arms the unit scheduler.
 static constexpr int kFinSlices = 32;
-static constexpr int kFinMaxPer = 40;  // partials per slice held in registers: grid <= 32 * 40 = 1280 CTAs
+static constexpr int kFinMaxPer = 8;   // tiles per slice held in registers: ntiles (= SM count) <= 32 * 8 = 256
 
 __global__ void __launch_bounds__(1024) head_finalize_kernel(
     float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
-    int nparts, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
+    int nparts, int ntiles, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
     double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err) {
   const int ndt = C * CKP;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -776,14 +779,14 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
 #pragma unroll
       for (int q = 0; q < kFinMaxPer; ++q) {
         const int g = ty + q * kFinSlices;
-        v[q] = (g < nparts) ? part_dT[(size_t)g * ndt + o] : 0.f;
+        v[q] = (g < ntiles) ? part_dT[(size_t)g * ndt + o] : 0.f;
       }
 #pragma unroll
       for (int q = 0; q < kFinMaxPer; ++q) s += (double)v[q];
 #pragma unroll
       for (int q = 0; q < kFinMaxPer; ++q) {
         const int g = ty + q * kFinSlices;
-        if (g < nparts) part_dT[(size_t)g * ndt + o] = 0.f;
+        if (g < ntiles) part_dT[(size_t)g * ndt + o] = 0.f;
       }
     }
     sm[ty][tx] = s;
@@ -844,8 +847,8 @@ __global__ void head_scale_kernel(float* __restrict__ dlogits, long long n, cons
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f32 x G*C*CKPmax]
-static constexpr int kMaxGridPerSm = 8;   // grid <= 148 * 8 = 1184 <= kFinSlices * kFinMaxPer
+// workspace: [counter u64 (+pad to 64 B)][part_loss f64 x G][part_cnt i64 x G][part_dT f32 x ntiles*C*CKP] (sized for G tiles)
+static constexpr int kMaxGridPerSm = 8;   // G = SM count * 8 bounds the grid (loss / count partials are per CTA)
 static constexpr int kMaxCKP = 64;
 
 struct Tuning { int ur, unused, threads, lpr; };
@@ -1021,13 +1024,14 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   A.part_loss = reinterpret_cast<double*>(ws + 64);
   A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
   A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
   if (mode != MODE_FWD)
     SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
   int grid = 0;
   rc = dispatch_all(mode, label_bytes, A, P, st, &grid);
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
-  head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, mode, gscale,
+  head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, mode, gscale,
                                               A.counter, stats, loss_mean, dT_out, err_flag);
   return (int)cudaGetLastError();
 }
@@ -1056,12 +1060,13 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
   A.part_loss = reinterpret_cast<double*>(ws + 64);
   A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
   A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
   SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
   int grid = 0;
   rc = dispatch_all(MODE_PLACE, 1, A, P, st, &grid);
   if (rc) return rc;
   // one block: loss / count partials and the scheduler re-arm (there are no dT tiles in this mode)
-  head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, CK, P.CKP, C, MODE_PLACE, 1.f,
+  head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, 0, CK, P.CKP, C, MODE_PLACE, 1.f,
                                            A.counter, stats, loss_mean, nullptr, nullptr);
   return (int)cudaGetLastError();
 }
