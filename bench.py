@@ -6,8 +6,9 @@
 
 A "step" is one pass of the hot path over one batch (BASELINE.json configs[1]: batch 8 per
 GPU, logits 19x65x129 -> 512x1024, C = 19 T-corrected CE, forward + backward):
-    memset(dLogits) -> fused fwd/bwd kernel -> finalize -> scale kernel (dLogits, dT *= 1 / N_valid); when
-    N > 1 the scale kernel first exchanges the 2.9 KB stats buffer with its peers over CUDA-IPC peer memory.
+    N = 1: label count + dLogits zeroing -> fused fwd/bwd kernel (applies 1 / N_valid itself) -> finalize;
+    N > 1: memset(dLogits) -> fused fwd/bwd kernel -> finalize -> scale kernel, which first exchanges the 2.9 KB
+    stats buffer with its peers over CUDA-IPC peer memory (dLogits, dT *= 1 / N_valid_global).
 `value`  : inputs already resident in HBM (rotating input sets larger than L2), timed with CUDA
            events, barrier + synchronize on both sides, max over ranks.  At N = 1 every step is one
            CUDA-graph replay (HeadRunner.graph_step); sharded runs too, with the stats exchange fused into
@@ -426,7 +427,7 @@ def run_ours(args, rank, local_rank, world):
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
                     "api": "simt_b200.HeadRunner.step on inputs uploaded by simt_b200.HostPrefetcher from pinned host memory; loss read back every step"},
             "gpu_launches": 3 * args.steps,
-            "launch": ("one CUDA graph replay per step (memset, head_kernel, head_finalize_kernel, head_scale_kernel)"
+            "launch": ("one CUDA graph replay per step (head_prep_kernel, head_kernel, head_finalize_kernel)"
                        if world == 1 else
                        ("one CUDA graph replay per step; the stats all-reduce is fused into the scale kernel over CUDA-IPC "
                         "peer memory (head_scale_xchg_kernel), no library collective"

@@ -212,6 +212,22 @@ int simt_head_scale_sharded(float* dlogits, long long n_dlogits, double* stats, 
                             void* const* mailboxes, int* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * simt_head_step: one whole training step of the head on ONE GPU, the form a training loop calls every
+ * iteration (the same reference lines as simt_head_fwdbwd + simt_head_scale, tools/trainV2_simt.py:
+ * 371-372,402-409,428), with the 1/N_valid scale resolved ON THE DEVICE BEFORE the fused kernel runs:
+ *   1. head_prep_kernel zeroes dlogits and counts the valid labels in one pass;
+ *   2. the fused kernel applies grad_out / N_valid to every dLogits contribution itself;
+ *   3. finalize writes loss, stats and the scaled dT.
+ * Three launches, no pass over dLogits after the kernel, no host sync, CUDA-graph capturable.
+ * grad_out: device scalar or NULL (= 1).  dlogits / dT / loss_mean are FINAL on return (stream order).
+ * (Sharded runs use simt_head_fwdbwd + simt_head_scale_sharded: one rendezvous per step, not two.)
+ * ------------------------------------------------------------------------- */
+int simt_head_step(const float* logits, int B, int CK, int h, int w, const float* T, int C,
+                   const void* labels, int label_bytes, int H, int W, int ignore,
+                   const float* grad_out, float* dlogits, float* dT, double* stats, float* loss_mean,
+                   int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Placeholder_loss (tools/trainV2_simt.py:202-230, called at :398-399 on the
  * upsampled prediction of :371-372), fused with the bilinear upsample and its backward like the head:
  * the [B, CK, H, W] tensor, its one-hot, `predict`, `predict_open` and their gradients are never

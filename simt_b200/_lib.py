@@ -45,6 +45,8 @@ SIGNATURES = {
     "simt_xchg_destroy": (c_int, [c_void_p]),
     "simt_head_scale_sharded": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                         c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
+    "simt_head_step": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "simt_placeholder_fwdbwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "simt_w_fit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_double, c_double,

@@ -46,7 +46,10 @@
 
 namespace simt {
 
-enum { MODE_FWD = 0, MODE_FWDBWD = 1, MODE_BWD = 2, MODE_PLACE = 3 };
+// MODE_STEP: forward + backward with the 1/N_valid scale known ON THE DEVICE before the kernel starts (a label-only
+// count pass), so dLogits leave the kernel final and there is no scale pass.  Single GPU only: sharded, the count
+// would be a second rendezvous per step on top of the stats exchange (measured slower than scaling after ONE exchange).
+enum { MODE_FWD = 0, MODE_FWDBWD = 1, MODE_BWD = 2, MODE_PLACE = 3, MODE_STEP = 4 };
 
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr double kLn2 = 0.6931471805599453094;
@@ -72,6 +75,9 @@ struct HeadArgs {
   int* err;
   int label_words_ok;  // uint8 labels: buffer 4-byte aligned and a multiple of 4 bytes long
   float place_thres, place_lambda;  // MODE_PLACE: confidence threshold (< 0: none), weight of the open-set term
+  // MODE_STEP: upstream gradient (device scalar or null = 1) and the valid-pixel count written by head_prep_kernel
+  const float* grad_out;
+  const double* count_local;
 };
 
 // ---- pixel <-> cell mapping, identical float arithmetic on host and device ----------
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   int* ys_tab = xs_tab + (A.ncx + 1);                                 // [ncy + 1] first pixel row of every cell-row
   __shared__ double red_d[NW];
   __shared__ long long red_i[NW];
+  __shared__ float s_gs;   // MODE_STEP: grad_out / N_valid (global)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -296,6 +303,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     if (k < CK) v = A.T ? __ldg(A.T + (size_t)k * C + y) : (k == y ? 1.f : 0.f);
     Ts[i] = -v;
   }
+  if (MODE == MODE_STEP && tid == 0)   // the valid-pixel count was produced by head_prep_kernel before this launch
+    s_gs = (float)((A.grad_out ? (double)__ldg(A.grad_out) : 1.0) / *A.count_local);
   for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
   for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
   unsigned smid;
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
             }
           } else if (last_cell) {
             float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
-            const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+            const float gs = (MODE == MODE_BWD) ? A.gscale : (MODE == MODE_STEP ? s_gs : 1.f);
             const float w0y = (1.f - ly) * gs, w1y = ly * gs;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
@@ -697,7 +706,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 
       if (BWD) {
         float* dst = A.dlogits + (size_t)b * CK * h * w;
-        const float gs = (MODE == MODE_BWD) ? A.gscale : 1.f;
+        const float gs = (MODE == MODE_BWD) ? A.gscale : (MODE == MODE_STEP ? s_gs : 1.f);
         if (cell_ok) {
           const unsigned plane = (unsigned)(h * w);
           float* d0 = dst + (size_t)kbase * plane + (gy0 * w + gx0);
@@ -756,6 +765,71 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   }
 }
 
+// Step prologue (MODE_STEP): zero dLogits and count this rank's valid pixels in ONE pass over the labels, so that the
+// main kernel can apply grad_out / N_valid itself.  The last block to finish publishes the count in `count_local`.
+// Validity is the main kernel's rule exactly: a class id below C that is not the ignore label.
+template <typename LabelT>
+__global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlogits, long long n_dl,
+                                                         const LabelT* __restrict__ labels, long long npix, int C,
+                                                         int ignore, unsigned long long* __restrict__ accum,
+                                                         unsigned long long* __restrict__ ticket,
+                                                         double* __restrict__ count_local) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // ---- zero dLogits ----
+  const long long n4 = ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) ? (n_dl >> 2) : 0;
+  float4* d4 = reinterpret_cast<float4*>(dlogits);
+  for (long long i = i0; i < n4; i += stride) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = n4 * 4 + i0; i < n_dl; i += stride) dlogits[i] = 0.f;
+  // ---- count valid labels ----
+  unsigned long long cnt = 0;
+  if (sizeof(LabelT) == 1) {
+    const int ign8 = (ignore >= 0 && ignore <= 255) ? ignore : 256;
+    const uint8_t* lb = reinterpret_cast<const uint8_t*>(labels);
+    const long long n16 = ((reinterpret_cast<uintptr_t>(lb) & 15) == 0) ? (npix >> 4) : 0;
+    const uint4* l4 = reinterpret_cast<const uint4*>(lb);
+    for (long long i = i0; i < n16; i += stride) {
+      const uint4 v = ldg_stream_u4(l4 + i);
+      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = (int)((wds[k] >> (8 * q)) & 0xffu);
+          cnt += (unsigned)((c < C) & (c != ign8));
+        }
+    }
+    for (long long i = n16 * 16 + i0; i < npix; i += stride) {
+      const int c = (int)__ldg(lb + i);
+      cnt += (unsigned)((c < C) & (c != ign8));
+    }
+  } else {
+    const long long* lb = reinterpret_cast<const long long*>(labels);
+    for (long long i = i0; i < npix; i += stride) {
+      const long long y = __ldg(lb + i);
+      cnt += (unsigned)((y >= 0) & (y < (long long)C) & (y != (long long)ignore));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  __shared__ unsigned long long s_w[8];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) b += s_w[k];
+    atomicAdd(accum, b);
+    __threadfence();
+    const unsigned long long t = atomicAdd(ticket, 1ULL);
+    if (t == (unsigned long long)gridDim.x - 1ULL) {      // last block: every partial is in
+      const unsigned long long total = atomicAdd(accum, 0ULL);
+      *accum = 0ULL;
+      *ticket = 0ULL;
+      *count_local = (double)total;
+    }
+  }
+}
+
 // Fixed-order reduction of the per-CTA partials.  blockDim = (32 outputs, 32 slices of the CTA range):
 // consecutive threads read consecutive tile entries (coalesced); every slice first issues ALL its loads
 // (independent, many in flight), sums them in order, then re-zeroes the entries for the next call; the
@@ -766,7 +840,8 @@ static constexpr int kFinMaxPer = 8;   // tiles per slice held in registers: nti
 __global__ void __launch_bounds__(1024) head_finalize_kernel(
     float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
     int nparts, int ntiles, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
-    double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err) {
+    double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err,
+    const float* __restrict__ grad_out, const double* __restrict__ count_dev) {
   const int ndt = C * CKP;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   __shared__ double sm[kFinSlices][33];
@@ -774,7 +849,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
   if ((int)blockIdx.x < (int)gridDim.x - 1) {
     const int o = blockIdx.x * 32 + tx;  // output index in the [y][k] layout of the tiles
     double s = 0.0;
-    if (o < ndt && (mode == MODE_FWDBWD || mode == MODE_BWD)) {
+    if (o < ndt && (mode == MODE_FWDBWD || mode == MODE_BWD || mode == MODE_STEP)) {
       float v[kFinMaxPer];
 #pragma unroll
       for (int q = 0; q < kFinMaxPer; ++q) {
@@ -798,7 +873,9 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
       const int y = o / CKP, k = o - y * CKP;
       if (k < CK) {
         if (stats) stats[2 + k * C + y] = -t;
-        if (dT_out) dT_out[k * C + y] = (float)(-t * (double)gscale);
+        // MODE_STEP on one GPU: grad_out / N_valid is already known on the device (count pass)
+        const double sc = count_dev ? (grad_out ? (double)__ldg(grad_out) : 1.0) / *count_dev : (double)gscale;
+        if (dT_out) dT_out[k * C + y] = (float)(-t * sc);
       }
     }
   } else {
@@ -916,6 +993,8 @@ static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid
 
 static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
   if (mode == MODE_PLACE) return dispatch<MODE_PLACE, uint8_t>(A, P, st, grid_out);
+  if (mode == MODE_STEP)
+    return label_bytes == 1 ? dispatch<MODE_STEP, uint8_t>(A, P, st, grid_out) : dispatch<MODE_STEP, long long>(A, P, st, grid_out);
   if (label_bytes == 1) {
     if (mode == MODE_FWD) return dispatch<MODE_FWD, uint8_t>(A, P, st, grid_out);
     if (mode == MODE_FWDBWD) return dispatch<MODE_FWDBWD, uint8_t>(A, P, st, grid_out);
@@ -1032,7 +1111,58 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
   head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, mode, gscale,
-                                              A.counter, stats, loss_mean, dT_out, err_flag);
+                                              A.counter, stats, loss_mean, dT_out, err_flag, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+// One whole training step of the head on one GPU (the path HeadRunner.step takes): label count + dLogits zeroing, the
+// fused kernel applying the final scale, finalize.  Three launches, no pass over dLogits after the kernel.
+static int run_step(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
+                    int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
+                    double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+  int rc = validate(logits, B, CK, h, w, C, labels, label_bytes, H, W, T);
+  if (rc) return rc;
+  if (!err_flag || !workspace || !dlogits || !stats) return SIMT_EINVAL;
+  if (workspace_bytes < simt_head_workspace_bytes(B, CK, C, h, w, H, W)) return SIMT_EWORKSPACE;
+  HeadArgs A{};
+  Plan P{};
+  A.logits = logits; A.T = T; A.labels = labels;
+  A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = ignore;
+  A.gscale = 1.f; A.dlogits = dlogits; A.err = err_flag; A.grad_out = grad_out;
+  A.label_words_ok = (label_bytes == 1 && (reinterpret_cast<uintptr_t>(labels) & 3) == 0 &&
+                      (((long long)B * H * W) & 3) == 0) ? 1 : 0;
+  rc = make_plan(MODE_STEP, B, CK, C, h, w, H, W, &A, &P);
+  if (rc) return rc;
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  A.counter = reinterpret_cast<unsigned long long*>(ws);
+  unsigned long long* accum = reinterpret_cast<unsigned long long*>(ws + 8);     // the 64-byte header has room
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws + 16);
+  double* count_local = reinterpret_cast<double*>(ws + 24);
+  A.count_local = count_local;
+  A.part_loss = reinterpret_cast<double*>(ws + 64);
+  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
+  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
+  const long long n_dl = (long long)B * CK * h * w, npix = (long long)B * H * W;
+  const int pgrid = di.sm_count * 4;
+  if (label_bytes == 1)
+    head_prep_kernel<uint8_t><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const uint8_t*>(labels), npix, C, ignore,
+                                                     accum, ticket, count_local);
+  else
+    head_prep_kernel<long long><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const long long*>(labels), npix, C,
+                                                       ignore, accum, ticket, count_local);
+  SIMT_CUDA_TRY(cudaGetLastError());
+  int grid = 0;
+  rc = dispatch_all(MODE_STEP, label_bytes, A, P, st, &grid);
+  if (rc) return rc;
+  const int fgrid = (C * P.CKP + 31) / 32 + 1;
+  head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, MODE_STEP,
+                                              1.f, A.counter, stats, loss_mean, dT, err_flag, grad_out, count_local);
   return (int)cudaGetLastError();
 }
 
@@ -1067,7 +1197,7 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
   if (rc) return rc;
   // one block: loss / count partials and the scheduler re-arm (there are no dT tiles in this mode)
   head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, 0, CK, P.CKP, C, MODE_PLACE, 1.f,
-                                           A.counter, stats, loss_mean, nullptr, nullptr);
+                                           A.counter, stats, loss_mean, nullptr, nullptr, nullptr, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -1110,6 +1240,13 @@ int simt_head_bwd(const float* logits, int B, int CK, int h, int w, const float*
                   void* workspace, size_t workspace_bytes, void* stream) {
   return run_head(MODE_BWD, logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, scale, dlogits, nullptr,
                   nullptr, dT, err_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int simt_head_step(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
+                   int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
+                   double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_step(logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, grad_out, dlogits, dT, stats, loss_mean,
+                  err_flag, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int simt_placeholder_fwdbwd(const float* logits, int B, int CK, int h, int w, int C, int H, int W, float thres,

@@ -17,47 +17,20 @@
 // mailbox and is advanced by the last block to finish, so the launch has no per-step host argument and the whole
 // step (memset, head kernel, finalize, this kernel) replays from a CUDA graph.  Waits are bounded: a peer that never
 // arrives sets SIMT_ERRBIT_XCHG_TIMEOUT instead of hanging the GPU.
-#include "common.cuh"
+#include "xchg.cuh"
 
 namespace simt {
-
-static constexpr int kMaxPeers = 8;
-static constexpr int kHdrWords = 32;  // u64: [0] step counter, [1] block ticket, [8 + parity * 8 + rank] flags
-static constexpr size_t kHdrBytes = kHdrWords * sizeof(unsigned long long);
-
-struct XchgArgs {
-  unsigned char* mail[kMaxPeers];  // mailbox base of every rank (mail[rank] is local memory)
-  int rank, world, n_stats;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ double* slot_of(unsigned char* mailbox, int parity, int rank, int n_stats) {
-  return reinterpret_cast<double*>(mailbox + kHdrBytes) + ((size_t)parity * kMaxPeers + rank) * n_stats;
-}
 
 __global__ void __launch_bounds__(256) head_scale_xchg_kernel(float* __restrict__ dlogits, long long n, double* stats,
                                                                int nT, const float* __restrict__ grad_out,
                                                                float* __restrict__ dT, float* __restrict__ loss_mean,
                                                                int* __restrict__ err, const XchgArgs X) {
   unsigned char* own = X.mail[X.rank];
-  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(own);
+  unsigned long long* hdr = hdr_of(own);
   __shared__ double s_cnt;
   __shared__ int s_timeout;
   const int tid = threadIdx.x;
-  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(hdr) + 1ULL;  // this step's number
+  const unsigned long long seq = step_seq(own);
   const int par = (int)(seq & 1ULL);
   if (tid == 0) s_timeout = 0;
 
@@ -70,21 +43,11 @@ __global__ void __launch_bounds__(256) head_scale_xchg_kernel(float* __restrict_
     __threadfence_system();
     __syncthreads();
     if (tid < X.world)
-      st_release_sys(reinterpret_cast<unsigned long long*>(X.mail[tid]) + 8 + par * kMaxPeers + X.rank, seq);
+      st_release_sys(hdr_of(X.mail[tid]) + kHdrStatFlag + par * kMaxPeers + X.rank, seq);
   }
   __syncthreads();
   // ---- wait for every rank's contribution to arrive in OUR mailbox (bounded) ----------------------
-  if (tid < X.world) {
-    const unsigned long long* f = hdr + 8 + par * kMaxPeers + tid;
-    long long spins = 0;
-    while (ld_acquire_sys(f) < seq) {
-      if (++spins > (1LL << 24)) {  // seconds, not the microseconds an exchange takes: the peer is gone
-        s_timeout = 1;
-        break;
-      }
-      __nanosleep(64);
-    }
-  }
+  if (tid < X.world && !wait_flag(hdr + kHdrStatFlag + par * kMaxPeers + tid, seq)) s_timeout = 1;  // the peer is gone
   __syncthreads();
   if (tid == 0) {
     double c = 0.0;

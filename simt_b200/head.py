@@ -199,10 +199,11 @@ class SimTHead(torch.nn.Module):
 class HeadRunner:
     """Static-shape, allocation-free form of the fused head for training loops and benchmarks.
 
-    All outputs are preallocated once; ``step`` enqueues memset + fused fwd/bwd kernel + finalize
-    [+ one all-reduce of the 2.9 KB stats buffer when ``group`` is given] + scale kernel, and
-    returns views (loss f32[], dlogits f32[B,CK,h,w], dT f32[CK,C]) without synchronising.
-    ``graph_step`` is the same work replayed from a CUDA graph.
+    All outputs are preallocated once; ``step`` enqueues, on one GPU, a label-count + zeroing pass, the fused
+    fwd/bwd kernel (which applies grad_out / N_valid itself) and finalize; sharded (``group``), memset + fused
+    kernel + finalize + a scale kernel that exchanges the 2.9 KB stats buffer with its peers first.  It returns views
+    (loss f32[], dlogits f32[B,CK,h,w], dT f32[CK,C]) without synchronising.  ``graph_step`` is the same work
+    replayed from a CUDA graph.
     """
 
     def __init__(self, B, CK, C, h, w, H, W, device=None, ignore=255, label_dtype=torch.uint8, group=None,
@@ -227,6 +228,10 @@ class HeadRunner:
         # sharded: the stats exchange is fused into the scale kernel over CUDA-IPC peer memory when every rank can
         # map every other rank's mailbox (one node); otherwise one library all-reduce per step
         self.mailbox = None
+        self._world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self._world = dist.get_world_size(group)
         if group is not None and exchange == "p2p":
             import torch.distributed as dist
             if dist.get_world_size(group) > 1:
@@ -267,25 +272,38 @@ class HeadRunner:
             _lib.check(rc, "simt_head_scale_sharded")
 
     def step(self, logits, T, labels, grad_out=None):
+        """One training step: (loss, dlogits, dT), final and global, without synchronising.
+        One GPU: ``simt_head_step`` (label count + zeroing, fused kernel applying grad_out / N itself, finalize).
+        Sharded: fwdbwd, then the scale kernel with the stats exchange fused in over the peer mailboxes (ONE
+        rendezvous per step), or -- fallback -- one NCCL all-reduce between fwdbwd and scale."""
         stream = _stream_ptr()
-        self.fwdbwd(logits, T, labels, stream)
-        if self.mailbox is not None:
-            self.scale_sharded(grad_out, stream)     # loss / stats / dT are global on return
+        if self._world > 1:
+            self.fwdbwd(logits, T, labels, stream)
+            if self.mailbox is not None:
+                self.scale_sharded(grad_out, stream)     # loss / stats / dT are global on return
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+                self.scale(grad_out, stream)
             return self.loss, self.dlogits, self.dT
-        if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
-        self.scale(grad_out, stream)
+        B, CK, C, h, w, H, W = self.shape
+        ws, nws, stats, loss, dl, dT, err = self._p
+        rc = self.lib.simt_head_step(logits.data_ptr(), B, CK, h, w, None if T is None else T.data_ptr(), C,
+                                     labels.data_ptr(), self.label_bytes, H, W, self.ignore,
+                                     None if grad_out is None else grad_out.data_ptr(), dl, dT, stats, loss, err, ws, nws,
+                                     stream)
+        if rc:
+            _lib.check(rc, "simt_head_step")
         return self.loss, self.dlogits, self.dT
 
     def graph_step(self, logits, T, labels, grad_out=None):
-        """``step`` replayed from a CUDA graph: memset + fused kernel + finalize + scale are captured ONCE for this exact
-        set of buffers (keyed by their addresses) and re-launched as one graph afterwards -- the four launches of a
-        step are launch-latency-bound next to a 90 us kernel.  The graph reads the buffers' CURRENT contents on every
+        """``step`` replayed from a CUDA graph: its three (one GPU) or four (sharded) launches are captured ONCE for this
+        exact set of buffers (keyed by their addresses) and re-launched as one graph afterwards -- they are
+        launch-latency-bound next to a 90 us kernel.  The graph reads the buffers' CURRENT contents on every
         replay (refill ``logits`` / ``labels`` / ``T`` in place).  Sharded runs replay too when the stats exchange is
         the fused peer-memory one (no library collective inside the graph); with the all-reduce fallback they take the
         eager path."""
-        if self.group is not None and self.mailbox is None:
+        if self._world > 1 and self.mailbox is None:
             return self.step(logits, T, labels, grad_out)
         key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
                None if grad_out is None else grad_out.data_ptr())

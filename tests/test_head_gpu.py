@@ -303,3 +303,32 @@ def test_host_prefetcher_double_buffering_delivers_every_batch():
     for i in range(5):
         ref = O.simt_head_loss(host[i][0], T, host[i][1].long(), (H, W))
         assert abs(float(losses[i]) - float(ref)) <= TOL * abs(float(ref)), i
+
+
+@pytest.mark.parametrize("int64_labels", [False, True])
+@pytest.mark.parametrize("K", [0, 4])
+def test_headrunner_step_device_side_scale(K, int64_labels):
+    """HeadRunner.step (simt_head_step: label count pass + fused kernel applying grad_out / N itself, no scale pass):
+    loss, dLogits, dT equal the oracle's, with and without an upstream gradient, for uint8 and int64 labels."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    B, CK, h, w, H, W = 3, 19 + K, 9, 17, 70, 133          # odd sizes: unaligned label rows, tail paths of the count pass
+    lg, lab = O.synth_head_inputs(B, CK, h, w, H, W, seed=11 + K, coherent=True, ignore_frac=0.15)
+    T = O.sig_ntm_forward(torch.randn(CK, 19, generator=torch.Generator().manual_seed(2)), class_dist(), 19, K)
+    ref = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+    r = simt_b200.HeadRunner(B, CK, 19, h, w, H, W, device=dev, label_dtype=torch.int64 if int64_labels else torch.uint8)
+    labd = (lab.long() if int64_labels else lab.to(torch.uint8)).to(dev)
+    for g in (None, 0.37):
+        go = None if g is None else torch.tensor(g, device=dev)
+        loss, dl, dT = r.step(lg.to(dev), T.to(dev), labd, grad_out=go)
+        s = 1.0 if g is None else g
+        assert abs(float(loss) - float(ref[0])) <= TOL * abs(float(ref[0]))
+        assert rel_l2(dl.cpu().numpy(), s * ref[1].numpy()) <= TOL
+        assert rel_l2(dT.cpu().numpy(), s * ref[2].numpy()) <= TOL
+        assert float(r.stats[1]) == float(((lab >= 0) & (lab < 19)).sum())
+    # nothing valid: mean over nothing -> NaN, like the reference
+    labd.fill_(255)
+    loss, dl, dT = r.step(lg.to(dev), T.to(dev), labd)
+    assert np.isnan(float(loss))
+    simt_b200.check_errors(dev)
