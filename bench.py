@@ -433,7 +433,7 @@ def run_ours(args, rank, local_rank, world):
                         "peer memory (head_scale_xchg_kernel), no library collective"
                         if runners[0].mailbox is not None else "eager launches + one NCCL all-reduce per step")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "simt::head_kernel<CPL=10,LPR=2,FWDBWD,uint8>",
+                         "traffic": ncu_traffic(), "kernel": "simt::head_kernel<CPL=10,LPR=2,MODE_STEP (N=1) | FWDBWD (N>1),uint8>",
                          "kernel_ms": k_avg_ms, "launches_timed": int(klaunches.value),
                          "kernel_timing": "CUDA events around head_kernel on its stream, the timed steps re-run eagerly right after the timed region",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch(B_PER_GPU), "peak_source": peak_src,
