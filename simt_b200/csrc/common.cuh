@@ -54,6 +54,36 @@ inline int ensure_dynamic_smem(Kernel kernel, bool (&done)[64], int bytes) {
   return 0;
 }
 
+// ---- pixel <-> cell mapping, identical float arithmetic on host and device ----------
+__host__ __device__ __forceinline__ float src_index(float scale, int X) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(scale, (float)X);  // no FMA contraction: torch rounds the product
+#else
+  volatile float r = scale * (float)X;
+  return r;
+#endif
+}
+__host__ __device__ __forceinline__ int cell_of(int X, float scale, int ncell) {
+  int c = (int)src_index(scale, X);  // src >= 0: truncation == floor
+  return c < ncell - 1 ? c : ncell - 1;
+}
+__host__ __device__ __forceinline__ float lambda_of(int X, float scale, int cell) {
+  float l = src_index(scale, X) - (float)cell;
+  l = l < 0.f ? 0.f : l;
+  return l > 1.f ? 1.f : l;
+}
+// first output index whose cell is >= c  (monotone in c; 0 for c<=0, OUT for c>=ncell)
+__host__ __device__ inline int first_px_of_cell(int c, float scale, int ncell, int OUT) {
+  if (c <= 0) return 0;
+  if (c >= ncell || !(scale > 0.f)) return OUT;
+  float guess = ceilf((float)c / scale);
+  int X = guess >= (float)OUT ? OUT : (int)guess;
+  if (X < 0) X = 0;
+  while (X > 0 && cell_of(X - 1, scale, ncell) >= c) --X;
+  while (X < OUT && cell_of(X, scale, ncell) < c) ++X;
+  return X;
+}
+
 // launch profiler (capi.cu)
 bool prof_enabled();
 void prof_begin(cudaStream_t st);

@@ -336,43 +336,92 @@ __global__ void __launch_bounds__(256) softmax_lo_kernel(const float* __restrict
   for (int k = 0; k < C; ++k) pb[(size_t)k * hw] = expf(xb[(size_t)k * hw] - m) / s;
 }
 
-// one pixel per thread: upsampled class posterior -> max / arg-max -> thresholds -> (student arg-max) -> uint8
+// One thread per (image, pixel row, low-res column x0): the run of output pixels whose left neighbour node is x0
+// (8 pixels at the training shape).  The four corner values of a channel are loaded ONCE per run and every pixel of
+// the run is evaluated with torch's unfused formula (same bits as a per-pixel gather, 1/8 of the loads):
+// upsampled class posterior -> max / arg-max -> thresholds -> (student arg-max) -> uint8.
+static constexpr int kRunPx = 8;
+
 __global__ void __launch_bounds__(256) pseudo_label_kernel(const float* __restrict__ probs_lo, const float* __restrict__ pred2_lo,
                                                             int B, int C, int CK, int h, int w, int H, int W, float sy,
                                                             float sx, float thr_hi, float thr_lo,
                                                             uint8_t* __restrict__ out) {
-  const long long npix = (long long)B * H * W;
+  const long long nthreads = (long long)B * H * w;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
-    const int X = (int)(p % W);
-    const long long t = p / W;
-    const int Y = (int)(t % H);
-    const int b = (int)(t / H);
-    const Bilin bl = bilin_setup(Y, X, h, w, sy, sx);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nthreads; t += stride) {
+    const int x0 = (int)(t % w);
+    const long long r = t / w;
+    const int Y = (int)(r % H);
+    const int b = (int)(r / H);
+    // pixels with min(floor(sx * X), w - 1) == x0
+    const int xa = first_px_of_cell(x0, sx, w, W);
+    const int xe = (x0 + 1 < w) ? first_px_of_cell(x0 + 1, sx, w, W) : W;
+    if (xa >= xe) continue;
+    const float fy = __fmul_rn(sy, (float)Y);
+    const int y0 = min((int)fy, h - 1), y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), ly0 = 1.f - ly1;
+    const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
     const float* base = probs_lo + (size_t)b * C * h * w;
-    float best = -INFINITY;
-    int bestk = 0;
-    for (int k = 0; k < C; ++k) {
-      const float z = bilin_eval(base + (size_t)k * h * w, bl);
-      if (z > best || k == 0) { best = z; bestk = k; }
-    }
-    int lab = (best > thr_hi) ? bestk : 255;          // :359
-    if (best < thr_lo) {                               // :361 -> low confidence: :387-393
-      lab = 255;
-      if (pred2_lo) {
-        const float* pb = pred2_lo + (size_t)b * CK * h * w;
-        float sb = -INFINITY;
-        int sk = 0;
-        for (int k = 0; k < CK; ++k) {
-          const float z = bilin_eval(pb + (size_t)k * h * w, bl);
-          if (z > sb || k == 0) { sb = z; sk = k; }
-        }
-        if (sk >= C) lab = sk;                         // an open-set placeholder class
-      } else {
-        lab = C;                                       // without the student: the raw marker of :361
+    const float* pb = pred2_lo ? pred2_lo + (size_t)b * CK * h * w : nullptr;
+    uint8_t* orow = out + ((size_t)b * H + Y) * W;
+    for (int xs = xa; xs < xe; xs += kRunPx) {
+      const int n = min(kRunPx, xe - xs);
+      float lx0[kRunPx], lx1[kRunPx], best[kRunPx];
+      int bestk[kRunPx];
+#pragma unroll
+      for (int j = 0; j < kRunPx; ++j) {
+        const float fx = __fmul_rn(sx, (float)(xs + j));
+        lx1[j] = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+        lx0[j] = 1.f - lx1[j];
+        best[j] = -INFINITY;
+        bestk[j] = 0;
       }
+      for (int k = 0; k < C; ++k) {
+        const float* pl = base + (size_t)k * h * w;
+        const float v00 = __ldg(pl + o00), v01 = __ldg(pl + o01), v10 = __ldg(pl + o10), v11 = __ldg(pl + o11);
+#pragma unroll
+        for (int j = 0; j < kRunPx; ++j) {
+          // w0h*(w0w*x00 + w1w*x01) + w1h*(w0w*x10 + w1w*x11), every product and sum rounded
+          const float top = __fadd_rn(__fmul_rn(lx0[j], v00), __fmul_rn(lx1[j], v01));
+          const float bot = __fadd_rn(__fmul_rn(lx0[j], v10), __fmul_rn(lx1[j], v11));
+          const float z = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+          if (z > best[j] || k == 0) { best[j] = z; bestk[j] = k; }
+        }
+      }
+      int lab[kRunPx];
+      bool low = false;
+#pragma unroll
+      for (int j = 0; j < kRunPx; ++j) {
+        lab[j] = (best[j] > thr_hi) ? bestk[j] : 255;        // :359
+        if (best[j] < thr_lo) {                              // :361 -> low confidence: :387-393
+          lab[j] = pb ? 255 : C;                             // without the student: the raw marker of :361
+          low = low || (j < n);
+        }
+      }
+      if (low && pb) {
+        float sb[kRunPx];
+        int sk[kRunPx];
+#pragma unroll
+        for (int j = 0; j < kRunPx; ++j) { sb[j] = -INFINITY; sk[j] = 0; }
+        for (int k = 0; k < CK; ++k) {
+          const float* pl = pb + (size_t)k * h * w;
+          const float v00 = __ldg(pl + o00), v01 = __ldg(pl + o01), v10 = __ldg(pl + o10), v11 = __ldg(pl + o11);
+#pragma unroll
+          for (int j = 0; j < kRunPx; ++j) {
+            const float top = __fadd_rn(__fmul_rn(lx0[j], v00), __fmul_rn(lx1[j], v01));
+            const float bot = __fadd_rn(__fmul_rn(lx0[j], v10), __fmul_rn(lx1[j], v11));
+            const float z = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+            if (z > sb[j] || k == 0) { sb[j] = z; sk[j] = k; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kRunPx; ++j)
+          if (best[j] < thr_lo && sk[j] >= C) lab[j] = sk[j];   // an open-set placeholder class
+      }
+#pragma unroll
+      for (int j = 0; j < kRunPx; ++j)
+        if (j < n) orow[xs + j] = (uint8_t)lab[j];
     }
-    out[p] = (uint8_t)lab;
   }
 }
 
@@ -394,7 +443,7 @@ extern "C" int simt_pseudo_labels(const float* fixed_logits_lo, const float* pre
   SIMT_CUDA_TRY(cudaGetLastError());
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  long long grid = ((long long)B * H * W + 255) / 256;
+  long long grid = ((long long)B * H * w + 255) / 256;          // one thread per (image, pixel row, low-res column)
   if (grid > (long long)di.sm_count * 16) grid = (long long)di.sm_count * 16;
   prof_begin(st);
   pseudo_label_kernel<<<(int)grid, 256, 0, st>>>(probs_scratch, pred2_lo, B, C, CK, h, w, H, W, sy, sx, thres_high,

@@ -217,3 +217,36 @@ def test_fit_w_rejects_what_it_does_not_implement():
         simt_b200.fit_w(ntm, wm, torch.optim.Adam(wm.parameters(), lr=0.1, weight_decay=0.01))
     with pytest.raises(ValueError):
         simt_b200.fit_w(ntm, wm, torch.optim.Adam(ntm.parameters(), lr=0.1))
+
+
+@pytest.mark.parametrize("h,w,H,W,student", [
+    (7, 6, 41, 29, True),      # odd sizes, ragged runs
+    (17, 33, 8, 16, True),     # down-sampling: most low-res columns own no output pixel
+    (12, 20, 12, 20, True),    # identity size: one pixel per run
+    (3, 2, 40, 70, True),      # 70-pixel runs: several chunks of 8 per thread
+    (1, 9, 1, 64, False),      # a single row, no student head (the raw marker C of :361)
+])
+def test_pseudo_labels_shapes_vs_oracle(h, w, H, W, student):
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(h * 100 + w)
+    B, C, CK = 2, 19, 23
+    fixed = 2.5 * torch.randn(B, C, h, w, generator=g)
+    pred2 = 2.0 * torch.randn(B, CK, h, w, generator=g)
+    got = simt_b200.pseudo_labels(fixed.to(dev), pred2.to(dev) if student else None, (H, W), C, 0.8, 0.2).cpu().long()
+    if student:
+        ref = O.pseudo_labels(fixed, O.upsample_bilinear_ac(pred2, (H, W)), (H, W), C, 0.8, 0.2)
+    else:   # :354-361 only
+        p = O.upsample_bilinear_ac(torch.softmax(fixed, 1), (H, W))
+        mx, am = p.max(1)
+        ref = torch.where(mx > 0.8, am, torch.full_like(am, 255))
+        ref = torch.where(mx < 0.2, torch.full_like(am, C), ref)
+    assert got.shape == ref.shape
+    probs = O.upsample_bilinear_ac(torch.softmax(fixed.double(), 1), (H, W))
+    top2 = probs.topk(2, dim=1).values
+    near = ((top2[:, 0] - 0.8).abs() < 1e-5) | ((top2[:, 0] - 0.2).abs() < 1e-5) | ((top2[:, 0] - top2[:, 1]) < 1e-5)
+    if student:
+        s2 = O.upsample_bilinear_ac(pred2.double(), (H, W)).topk(2, dim=1).values
+        near = near | ((s2[:, 0] - s2[:, 1]) < 1e-5)
+    assert not bool(((got != ref) & ~near).any())
