@@ -457,33 +457,103 @@ extern "C" int simt_pseudo_labels(const float* fixed_logits_lo, const float* pre
 // ---------------------------------------------------------------------------------------------------
 namespace simt {
 
+// One thread per (image, pixel row, column x0 of the FIRST scale): a run of output pixels (8 at the evaluation shape)
+// shares the four corners of scale a; of scale b it needs at most three neighbouring columns when b's cells are not
+// narrower than the run (the two-scale case of evaluate_cityscapes.py: 129x257 and 81x161 -> 1024x2048), otherwise b
+// falls back to one gather per pixel.  Every pixel is evaluated with torch's unfused formula on the same corner
+// values as a per-pixel gather (identical bits, ~1/6 of the loads).
 __global__ void __launch_bounds__(256) eval_argmax_kernel(const float* __restrict__ la, int CKa, int ha, int wa,
                                                            const float* __restrict__ lb, int CKb, int hb, int wb, int B,
                                                            int C, int H, int W, float sya, float sxa, float syb,
                                                            float sxb, uint8_t* __restrict__ pred) {
-  const long long npix = (long long)B * H * W;
+  const long long nthreads = (long long)B * H * wa;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
-    const int X = (int)(p % W);
-    const long long t = p / W;
-    const int Y = (int)(t % H);
-    const int b = (int)(t / H);
-    const Bilin ba = bilin_setup(Y, X, ha, wa, sya, sxa);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nthreads; t += stride) {
+    const int x0 = (int)(t % wa);
+    const long long r = t / wa;
+    const int Y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int xa = first_px_of_cell(x0, sxa, wa, W);
+    const int xe = (x0 + 1 < wa) ? first_px_of_cell(x0 + 1, sxa, wa, W) : W;
+    if (xa >= xe) continue;
+    // scale a: rows and the run's two columns
+    const float fya = __fmul_rn(sya, (float)Y);
+    const int ya0 = min((int)fya, ha - 1), ya1 = ya0 + (ya0 < ha - 1), x1 = x0 + (x0 < wa - 1);
+    const float lya1 = fminf(fmaxf(fya - (float)ya0, 0.f), 1.f), lya0 = 1.f - lya1;
+    const int a00 = ya0 * wa + x0, a01 = ya0 * wa + x1, a10 = ya1 * wa + x0, a11 = ya1 * wa + x1;
     const float* pa = la + (size_t)b * CKa * ha * wa;
-    Bilin bb = ba;
-    const float* pb = nullptr;
-    if (lb) {
-      bb = bilin_setup(Y, X, hb, wb, syb, sxb);
-      pb = lb + (size_t)b * CKb * hb * wb;
+    // scale b: rows
+    const float* pb = lb ? lb + (size_t)b * CKb * hb * wb : nullptr;
+    int yb0 = 0, yb1 = 0;
+    float lyb1 = 0.f, lyb0 = 1.f;
+    if (pb) {
+      const float fyb = __fmul_rn(syb, (float)Y);
+      yb0 = min((int)fyb, hb - 1); yb1 = yb0 + (yb0 < hb - 1);
+      lyb1 = fminf(fmaxf(fyb - (float)yb0, 0.f), 1.f); lyb0 = 1.f - lyb1;
     }
-    float best = -INFINITY;
-    int bestk = 0;
-    for (int k = 0; k < C; ++k) {
-      float z = bilin_eval(pa + (size_t)k * ha * wa, ba);
-      if (pb) z = __fadd_rn(z, bilin_eval(pb + (size_t)k * hb * wb, bb));   // the reference adds in fp32 on the host
-      if (z > best || k == 0) { best = z; bestk = k; }                       // first maximum, like np.argmax
+    uint8_t* orow = pred + ((size_t)b * H + Y) * W;
+    for (int xs = xa; xs < xe; xs += kRunPx) {
+      const int n = min(kRunPx, xe - xs);
+      float lx0[kRunPx], lx1[kRunPx], bx0[kRunPx], bx1[kRunPx], best[kRunPx];
+      int bestk[kRunPx], ob[kRunPx];
+      int c0 = 0;
+      bool near3 = true;   // b's columns of this chunk are within {c0, c0 + 1}
+#pragma unroll
+      for (int j = 0; j < kRunPx; ++j) {
+        const float fx = __fmul_rn(sxa, (float)(xs + j));
+        lx1[j] = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+        lx0[j] = 1.f - lx1[j];
+        best[j] = -INFINITY;
+        bestk[j] = 0;
+        bx0[j] = 1.f; bx1[j] = 0.f; ob[j] = 0;
+        if (pb) {
+          const float fxb = __fmul_rn(sxb, (float)(xs + j));
+          const int xb = min((int)fxb, wb - 1);
+          if (j == 0) c0 = xb;
+          bx1[j] = fminf(fmaxf(fxb - (float)xb, 0.f), 1.f);
+          bx0[j] = 1.f - bx1[j];
+          ob[j] = xb - c0;
+          if (j < n && ob[j] > 1) near3 = false;
+        }
+      }
+      const int cb0 = min(c0, wb - 1), cb1 = min(c0 + 1, wb - 1), cb2 = min(c0 + 2, wb - 1);
+      for (int k = 0; k < C; ++k) {
+        const float* pl = pa + (size_t)k * ha * wa;
+        const float v00 = __ldg(pl + a00), v01 = __ldg(pl + a01), v10 = __ldg(pl + a10), v11 = __ldg(pl + a11);
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
+        const float* ql = pb ? pb + (size_t)k * hb * wb : nullptr;
+        if (pb && near3) {
+          t0 = __ldg(ql + yb0 * wb + cb0); t1 = __ldg(ql + yb0 * wb + cb1); t2 = __ldg(ql + yb0 * wb + cb2);
+          u0 = __ldg(ql + yb1 * wb + cb0); u1 = __ldg(ql + yb1 * wb + cb1); u2 = __ldg(ql + yb1 * wb + cb2);
+        }
+#pragma unroll
+        for (int j = 0; j < kRunPx; ++j) {
+          // w0h*(w0w*x00 + w1w*x01) + w1h*(w0w*x10 + w1w*x11), every product and sum rounded
+          const float top = __fadd_rn(__fmul_rn(lx0[j], v00), __fmul_rn(lx1[j], v01));
+          const float bot = __fadd_rn(__fmul_rn(lx0[j], v10), __fmul_rn(lx1[j], v11));
+          float z = __fadd_rn(__fmul_rn(lya0, top), __fmul_rn(lya1, bot));
+          if (pb) {
+            float l0, r0, l1, r1;
+            if (near3) {
+              const bool o = ob[j] != 0;
+              l0 = o ? t1 : t0; r0 = o ? t2 : t1;
+              l1 = o ? u1 : u0; r1 = o ? u2 : u1;
+            } else {   // b's cells are narrower than the run: plain gather for this pixel
+              const int xb = min(c0 + ob[j], wb - 1), xb1 = xb + (xb < wb - 1);
+              l0 = __ldg(ql + yb0 * wb + xb); r0 = __ldg(ql + yb0 * wb + xb1);
+              l1 = __ldg(ql + yb1 * wb + xb); r1 = __ldg(ql + yb1 * wb + xb1);
+            }
+            const float tb = __fadd_rn(__fmul_rn(bx0[j], l0), __fmul_rn(bx1[j], r0));
+            const float bb = __fadd_rn(__fmul_rn(bx0[j], l1), __fmul_rn(bx1[j], r1));
+            z = __fadd_rn(z, __fadd_rn(__fmul_rn(lyb0, tb), __fmul_rn(lyb1, bb)));   // the reference adds in fp32 on the host
+          }
+          if (z > best[j] || k == 0) { best[j] = z; bestk[j] = k; }                    // first maximum, like np.argmax
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kRunPx; ++j)
+        if (j < n) orow[xs + j] = (uint8_t)bestk[j];
     }
-    pred[p] = (uint8_t)bestk;
   }
 }
 
@@ -499,7 +569,7 @@ extern "C" int simt_eval_argmax(const float* logits_a, int CKa, int ha, int wa, 
   int rc = device_info(&di);
   if (rc) return rc;
   auto sc = [](int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; };
-  long long grid = ((long long)B * H * W + 255) / 256;
+  long long grid = ((long long)B * H * wa + 255) / 256;       // one thread per (image, pixel row, column of scale a)
   if (grid > (long long)di.sm_count * 16) grid = (long long)di.sm_count * 16;
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(st);

@@ -186,3 +186,28 @@ def test_fused_eval_argmax_and_miou(two_scale):
     lab = O.label_mapping(gt, np.array(O.CITYSCAPES_LABEL2TRAIN))
     ref_hist = O.fast_hist(lab.flatten(), ref.flatten().astype(np.int64), 19)
     assert np.abs(m.value() - ref_hist).sum() <= 2 * int(diff.sum())
+
+
+@pytest.mark.parametrize("sa,sb,size", [
+    ((33, 65), (21, 41), (256, 512)),     # evaluate_cityscapes.py's ratio: the second scale is coarser (three-column path)
+    ((9, 12), (14, 23), (70, 95)),        # odd sizes, second scale finer (per-pixel gather path)
+    ((17, 33), None, (8, 16)),            # down-sampling, one scale
+    ((5, 4), (3, 2), (5, 4)),             # identity size for the first scale
+    ((2, 3), (1, 1), (40, 100)),          # 50-pixel runs, a 1x1 second scale
+])
+def test_eval_argmax_shapes_vs_oracle(sa, sb, size):
+    import simt_b200
+    from oracle import simt_oracle as O
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(sa[0] * 10 + sa[1])
+    a = 3.0 * torch.randn(2, 23, *sa, generator=g)
+    b = None if sb is None else 3.0 * torch.randn(2, 23, *sb, generator=g)
+    ref = O.eval_two_scale_argmax(a, b, size, 19)
+    got = simt_b200.eval_argmax(a.to(dev), None if b is None else b.to(dev), size, 19).cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == np.uint8
+    z = O.upsample_bilinear_ac(a[:, :19].double(), size)
+    if b is not None:
+        z = z + O.upsample_bilinear_ac(b[:, :19].double(), size)
+    top2 = z.topk(2, dim=1).values
+    near_tie = ((top2[:, 0] - top2[:, 1]) < 1e-4).numpy()
+    assert not ((got != ref) & ~near_tie).any()
