@@ -122,7 +122,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(n_sets, seed0, device=None, pin=False):
-    from oracle import simt_oracle as O          # input synthesis only (seeded)
+    from simt_b200 import synth as O              # seeded workload generator; not the oracle
     cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
     sets = []
     for s in range(n_sets):
@@ -249,9 +249,10 @@ def run_eval_confusion(lib, dev):
     2048x1024 val images (raw Cityscapes ids through the label2train LUT vs uint8 predictions), two
     launches of 250 images; bit-exactness checked against the numpy oracle on the distinct images."""
     import simt_b200
-    from oracle import simt_oracle as O
-    mapping = np.array(O.CITYSCAPES_LABEL2TRAIN)
-    base = [O.synth_eval_pair(1024, 2048, seed=50 + i, coherent=True, block=(96, 160), noise=0.0) for i in range(10)]
+    from simt_b200 import synth
+    from oracle import simt_oracle as O          # checker only: the numpy reference of the confusion matrix
+    mapping = np.array(synth.CITYSCAPES_LABEL2TRAIN)
+    base = [synth.synth_eval_pair(1024, 2048, seed=50 + i, coherent=True, block=(96, 160), noise=0.0) for i in range(10)]
     ref = np.zeros((19, 19), dtype=np.int64)
     for gt, pr in base:
         ref += O.fast_hist(O.label_mapping(gt, mapping).flatten(), pr.flatten(), 19)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import simt_b200  # noqa: E402
 from simt_b200 import _lib, head  # noqa: E402
-from oracle import simt_oracle as O  # noqa: E402  (input synthesis only)
+from simt_b200 import synth as O  # seeded workload generators
 
 PEAK = 6559.7
 try:

@@ -3,7 +3,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import simt_b200
 from simt_b200 import _lib
-from oracle import simt_oracle as O
+from simt_b200 import synth as O  # seeded workload generators
 lib = _lib.load(); dev = torch.device("cuda")
 cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
 lg, lab = O.synth_head_inputs(8, 19, 65, 129, 512, 1024, seed=1, coherent=True, class_dist=cd, block=(36, 52))

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import simt_b200
 from simt_b200 import _lib, head
-from oracle import simt_oracle as O
+from simt_b200 import synth as O  # seeded workload generators
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 BLOCK = (36, 52) if (len(sys.argv) <= 3 or sys.argv[3] != 'aligned') else 32

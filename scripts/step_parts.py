@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import simt_b200
 from simt_b200 import _lib
-from oracle import simt_oracle as O
+from simt_b200 import synth as O  # seeded workload generators
 lib = _lib.load(); dev = torch.device("cuda")
 cd = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "simt_b200", "data", "ClassDist_bapa.npy"))
 torch.manual_seed(1234); T = simt_b200.sig_NTM(19, 0).to(dev)().detach()

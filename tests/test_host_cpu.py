@@ -104,3 +104,22 @@ def test_torch_regulariser_expressions_match_reference():
         volume = simt_b200.volume_loss([T1, T2])
         assert abs(float(convex) - float(g["convex"])) <= 1e-5 * abs(float(g["convex"]))
         assert abs(float(volume) - float(g["volume"])) <= 1e-5 * abs(float(g["volume"]))
+
+
+def test_workload_generators_are_shared_not_oracle_code():
+    """bench.py's GPU leg and the profiling scripts take their seeded inputs from simt_b200.synth, never from oracle/;
+    the oracle re-exports the same generators for the tests, and the Cityscapes table is the same data in both."""
+    import re
+    from oracle import simt_oracle as O
+    from simt_b200 import synth
+    assert O.synth_head_inputs is synth.synth_head_inputs and O.synth_eval_pair is synth.synth_eval_pair
+    assert O.CITYSCAPES_LABEL2TRAIN == synth.CITYSCAPES_LABEL2TRAIN
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in os.listdir(os.path.join(root, "scripts")):
+        if f.endswith(".py"):
+            src = open(os.path.join(root, "scripts", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"scripts/{f} imports oracle/"
+    for f in os.listdir(os.path.join(root, "simt_b200")):
+        if f.endswith(".py"):
+            src = open(os.path.join(root, "simt_b200", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"simt_b200/{f} imports oracle/"
