@@ -10,7 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 BLOCK = (36, 52) if (len(sys.argv) <= 3 or sys.argv[3] != 'aligned') else 32
 lib = _lib.load(); dev = torch.device("cuda")
-RS = int(os.environ.get('SIMT_RS', '0')); lib.simt_head_set_tuning(0, RS, 0, 0)
+RS = int(os.environ.get('SIMT_RS', '0')); FL = int(os.environ.get('SIMT_FLAGS', '0')); LP = int(os.environ.get('SIMT_LPR', '0')); lib.simt_head_set_tuning(0, RS, FL, LP)
 cd = np.load(os.path.join(ROOT, "simt_b200", "data", "ClassDist_bapa.npy"))
 torch.manual_seed(1234); T = simt_b200.sig_NTM(19, K).to(dev)().detach()
 res = []
@@ -23,4 +23,4 @@ for coh in (True, False):
         torch.cuda.synchronize()
         ms, n = ctypes.c_double(), ctypes.c_longlong(); lib.simt_b200_profile_read(ctypes.byref(ms), ctypes.byref(n)); lib.simt_b200_profile_enable(0)
         res.append(f"{'coh' if coh else 'rnd'}-{'fwdbwd' if ng else 'fwd'}={ms.value / n.value * 1e3:.1f}us")
-print(os.environ.get("SIMT_B200_LIB", "default").split("/")[-1], f"rs={RS}", f"B={B} K={K}", " ".join(res), flush=True)
+print(os.environ.get("SIMT_B200_LIB", "default").split("/")[-1], f"small_pct={RS} flags={FL} lpr={LP}", f"B={B} K={K}", " ".join(res), flush=True)

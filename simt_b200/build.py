@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 LIB_PATH = os.path.join(HERE, "libsimt_b200.so")
-SOURCES = ["capi.cu", "head.cu", "hist.cu", "nll2d.cu", "reg.cu", "wfit.cu", "xchg.cu"]
+SOURCES = ["capi.cu", "head.cu", "head_ident.cu", "hist.cu", "nll2d.cu", "reg.cu", "wfit.cu", "xchg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

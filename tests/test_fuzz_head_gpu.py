@@ -1,0 +1,106 @@
+"""Randomised GPU parity sweep.  pytest (-m gpu) runs a bounded number of cases; by hand for a longer sweep:
+    python tests/test_fuzz_head_gpu.py [n_cases] [seed]
+Random shapes (up-, down- and identity-sampling, odd sizes, 1-wide / 1-high tensors), channel counts, label patterns and
+entry points (autograd simt_head, HeadRunner.step, Placeholder_loss) against the fp64 oracle at the 1e-5 bar."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import simt_b200  # noqa: E402
+from oracle import simt_oracle as O  # noqa: E402
+from util import rel_l2  # noqa: E402
+
+import pytest  # noqa: E402
+
+TOL = 1e-5
+
+
+def run_fuzz(n_cases, seed):
+    """(worst errors, list of failure descriptions) over n_cases random cases."""
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda")
+    worst = {"loss": 0.0, "dl": 0.0, "dT": 0.0}
+    fails = []
+    for case in range(n_cases):
+        K = int(rng.choice([0, 0, 4, 4, 15, 1, 9]))
+        C, CK = 19, 19 + K
+        B = int(rng.integers(1, 4))
+        h, w = int(rng.integers(1, 20)), int(rng.integers(1, 24))
+        mode = rng.choice(["up", "up", "up", "same", "down"])
+        if mode == "up":
+            H, W = h * int(rng.integers(1, 9)) + int(rng.integers(0, 5)), w * int(rng.integers(1, 9)) + int(rng.integers(0, 5))
+        elif mode == "same":
+            H, W = h, w
+        else:
+            H, W = max(1, h // 2), max(1, w // 2 + 1)
+        coherent = bool(rng.integers(0, 2))
+        ign = float(rng.choice([0.0, 0.1, 0.5]))
+        scale = float(rng.choice([0.5, 3.0, 12.0]))
+        seed = int(rng.integers(0, 1 << 30))
+        lg, lab = O.synth_head_inputs(B, CK, h, w, H, W, seed=seed, coherent=coherent, ignore_frac=ign,
+                                      block=(int(rng.integers(1, 12)), int(rng.integers(1, 12))), logit_scale=scale)
+        if not bool(((lab >= 0) & (lab < C)).any()):
+            continue
+        T = O.sig_ntm_forward(torch.randn(CK, C, generator=torch.Generator().manual_seed(seed)), np.full(19, 1 / 19), C, K)
+        entry = rng.choice(["autograd", "step", "step64", "place"])
+        tag = f"case {case}: {entry} B={B} K={K} {h}x{w}->{H}x{W} coh={coherent} ign={ign} scale={scale} seed={seed}"
+        try:
+            if entry == "place":
+                thres = None if rng.integers(0, 2) else 0.5
+                ref_l, ref_dl = O.placeholder_fwd_bwd(lg, (H, W), C, K, thres, 0.1, torch.float64)
+                if not np.isfinite(float(ref_l)):
+                    continue
+                x = lg.to(dev).requires_grad_(True)
+                loss = simt_b200.Placeholder_loss(x, C, K, thres, out_size=(H, W), lambda_place=0.1)
+                loss.backward()
+                errs = {"loss": abs(float(loss.detach()) - float(ref_l)) / abs(float(ref_l)), "dl": rel_l2(x.grad.cpu().numpy(), ref_dl.numpy()), "dT": 0.0}
+                if max(errs.values()) > TOL:
+                    # the arg-max / threshold of this loss is discontinuous: when a pixel sits within fp32 rounding of a tie,
+                    # the reference's own fp32 run differs from its fp64 run by O(1/N); accept agreement with EITHER
+                    l32, d32 = O.placeholder_fwd_bwd(lg, (H, W), C, K, thres, 0.1, torch.float32)
+                    e32 = {"loss": abs(float(loss.detach()) - float(l32)) / abs(float(l32)), "dl": rel_l2(x.grad.cpu().numpy(), d32.numpy()), "dT": 0.0}
+                    if max(e32.values()) <= TOL:
+                        errs = e32
+            else:
+                ref_l, ref_dl, ref_dT = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+                if entry == "autograd":
+                    x, Tt = lg.to(dev).requires_grad_(True), T.to(dev).requires_grad_(True)
+                    loss = simt_b200.simt_head(x, Tt, lab.to(torch.uint8).to(dev), (H, W))
+                    loss.backward()
+                    dl, dT = x.grad, Tt.grad
+                else:
+                    i64 = entry == "step64"
+                    r = simt_b200.HeadRunner(B, CK, C, h, w, H, W, device=dev, label_dtype=torch.int64 if i64 else torch.uint8)
+                    loss, dl, dT = r.step(lg.to(dev), T.to(dev), (lab.long() if i64 else lab.to(torch.uint8)).to(dev))
+                errs = {"loss": abs(float(loss) - float(ref_l)) / abs(float(ref_l)), "dl": rel_l2(dl.cpu().numpy(), ref_dl.numpy()),
+                        "dT": rel_l2(dT.cpu().numpy(), ref_dT.numpy())}
+            simt_b200.check_errors(dev)
+        except Exception as e:   # noqa: BLE001
+            fails.append(f"{tag}: EXCEPTION {type(e).__name__}: {e}")
+            continue
+        for k, v in errs.items():
+            worst[k] = max(worst[k], v)
+        if max(errs.values()) > TOL or not all(np.isfinite(v) for v in errs.values()):
+            fails.append(f"{tag}: {errs}")
+    return worst, fails
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fuzz_head(seed):
+    worst, fails = run_fuzz(120, seed)
+    assert not fails, "\n".join(fails)
+
+
+if __name__ == "__main__":
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    worst, fails = run_fuzz(n_cases, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(f"{n_cases} cases, worst rel err loss/dlogits/dT = {worst['loss']:.2e}/{worst['dl']:.2e}/{worst['dT']:.2e}, {len(fails)} failures")
+    for f in fails:
+        print("FAIL", f)
+    sys.exit(1 if fails else 0)

@@ -332,3 +332,21 @@ def test_headrunner_step_device_side_scale(K, int64_labels):
     loss, dl, dT = r.step(lg.to(dev), T.to(dev), labd)
     assert np.isnan(float(loss))
     simt_b200.check_errors(dev)
+
+
+@pytest.mark.parametrize("gap", [60.0, 200.0, 1000.0])
+def test_plain_ce_huge_margin_is_finite_like_log_softmax(gap):
+    """T = None with the label's logit far below the maximum: p_y underflows in fp32 but torch's cross entropy
+    (log_softmax) stays finite -- loss = the gap, dlogits = p - onehot (utils/loss.py:35-36 -> F.cross_entropy)."""
+    from oracle import simt_oracle as O
+    logits, labels = O.synth_head_inputs(1, 19, 5, 9, 32, 64, seed=11, coherent=True, block=8, ignore_frac=0.1)
+    logits = logits * 0.5
+    logits[:, 3] += gap          # channel 3 dominates everywhere; most labels are other classes
+    lg = logits.clone().requires_grad_(True)
+    ref = O.plain_ce_loss(lg, labels.long(), (32, 64))
+    ref.backward()
+    assert np.isfinite(float(ref))
+    loss, dl, _ = run_gpu_head(logits.numpy(), None, labels.numpy(), (32, 64))
+    assert np.isfinite(float(loss)) and np.isfinite(dl).all()
+    assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
+    _check(dl, lg.grad.numpy(), "dlogits")
