@@ -43,7 +43,7 @@ enum {
 
 #define SIMT_ERRBIT_LABEL_RANGE 1 /* head: label not ignore and not in [0, C)        */
 #define SIMT_ERRBIT_PRED_RANGE  2 /* histograms: n_cols*a+b outside [0, rows*cols)   */
-#define SIMT_ERRBIT_XCHG_TIMEOUT 4 /* sharded scale: a peer's stats never arrived       */
+#define SIMT_ERRBIT_XCHG_TIMEOUT 4 /* sharded step: a peer's count / stats never arrived  */
 
 int         simt_b200_abi_version(void);
 const char* simt_b200_strerror(int code);
@@ -184,32 +184,45 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
                          const long long* pixel_idx, int n, float* rows, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * Sharded step (one process per GPU, batch split over the ranks of ONE node): the all-reduce of
- * `stats` fused into the scale kernel over peer memory (NVLink / NVSwitch P2P stores) instead of
- * a library collective between finalize and scale.  The reference is single-process: its
- * loss.backward() (tools/trainV2_simt.py:408-409,428) sees the whole batch, so the mean is over
- * the GLOBAL valid-pixel count and dT is summed over ranks.
+ * Sharded step (one process per GPU, batch split over the ranks of ONE node, world <= 8).  The
+ * reference is single-process: its loss.backward() (tools/trainV2_simt.py:408-409,428) sees the
+ * whole batch, so the mean is over the GLOBAL valid-pixel count and dT is summed over ranks.  The
+ * two tiny exchanges of a step (8-byte valid counts; the 2 + CK*C doubles of `stats`) travel over
+ * peer memory (NVLink / NVSwitch P2P stores into CUDA-IPC mapped mailboxes) from inside the step's
+ * own kernels -- no library collective, no extra launch, no pass over dLogits.
  *
  * simt_xchg_create: cudaMalloc + zero a mailbox of simt_xchg_bytes(2 + CK*C) bytes on the current
  *   device and export its 64-byte CUDA IPC handle.  The caller exchanges the handles (any
  *   transport: torch.distributed all-gather, MPI, a pipe) and opens every peer's mailbox with
  *   simt_xchg_open (current device = the opener's GPU).  close / destroy undo open / create.
- * simt_head_scale_sharded: replaces { all-reduce(stats); simt_head_scale } after simt_head_fwdbwd.
+ * simt_head_step_sharded: simt_head_step (below) on this rank's batch shard, with
+ *   dlogits = raw * g / N_global, dT = sum_ranks raw dT * g / N_global, loss_mean = the global mean
+ *   and `stats` = the all-reduced buffer (summed in rank order: the same bits on every rank).
+ *     1. head_prep_kernel zeroes dlogits, counts this rank's valid labels and pushes the count into
+ *        every peer's mailbox;
+ *     2. the fused kernel acquires the `world` counts right before its first dLogits update (a
+ *        late peer costs nothing until then) and applies g / N_global itself;
+ *     3. finalize pushes this rank's stats, waits for the peers' and writes loss / dT / stats.
  *   mailboxes: HOST array [world] of device pointers, mailboxes[rank] = this rank's own.
- *   On return (stream order) stats holds the all-reduced values (same bits on every rank),
- *   dlogits = raw * g / N_global, dT = sum_ranks raw dT * g / N_global, loss_mean the global mean.
- *   Every rank must call it once per step, in the same order; world <= 8.  No host-side step
- *   argument: the call sequence can be captured in a CUDA graph.  A peer that never arrives sets
- *   SIMT_ERRBIT_XCHG_TIMEOUT in err_flag after a bounded wait instead of hanging.
+ *   Every rank must call it once per step, in the same order.  No host-side step argument: the
+ *   call sequence can be captured in a CUDA graph.
+ * simt_xchg_set_timeout: bound of every in-kernel wait, in polls of ~64 ns (default 2^28, about
+ *   half a minute; <= 0 waits for ever).  A peer that does not arrive in time poisons this rank's
+ *   loss_mean, dT, stats (and, when the count is missing, dlogits) with NaN and sets
+ *   SIMT_ERRBIT_XCHG_TIMEOUT in err_flag: a rank never continues with a partial sum.  Ranks must
+ *   not drift further apart than the bound (raise it around checkpoints / evaluation on one rank).
  * ------------------------------------------------------------------------- */
 size_t simt_xchg_bytes(int n_stats);
 int simt_xchg_create(size_t bytes, void** mailbox, unsigned char* handle64);
 int simt_xchg_open(const unsigned char* handle64, void** peer_mailbox);
 int simt_xchg_close(void* peer_mailbox);
 int simt_xchg_destroy(void* mailbox);
-int simt_head_scale_sharded(float* dlogits, long long n_dlogits, double* stats, int CK, int C,
-                            const float* grad_out, float* dT, float* loss_mean, int rank, int world,
-                            void* const* mailboxes, int* err_flag, void* stream);
+void simt_xchg_set_timeout(long long max_spins);
+int simt_head_step_sharded(const float* logits, int B, int CK, int h, int w, const float* T, int C,
+                           const void* labels, int label_bytes, int H, int W, int ignore,
+                           const float* grad_out, float* dlogits, float* dT, double* stats, float* loss_mean,
+                           int* err_flag, void* workspace, size_t workspace_bytes,
+                           int rank, int world, void* const* mailboxes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * simt_head_step: one whole training step of the head on ONE GPU, the form a training loop calls every
@@ -220,7 +233,7 @@ int simt_head_scale_sharded(float* dlogits, long long n_dlogits, double* stats, 
  *   3. finalize writes loss, stats and the scaled dT.
  * Three launches, no pass over dLogits after the kernel, no host sync, CUDA-graph capturable.
  * grad_out: device scalar or NULL (= 1).  dlogits / dT / loss_mean are FINAL on return (stream order).
- * (Sharded runs use simt_head_fwdbwd + simt_head_scale_sharded: one rendezvous per step, not two.)
+ * (Batch-sharded runs: simt_head_step_sharded above.)
  * ------------------------------------------------------------------------- */
 int simt_head_step(const float* logits, int B, int CK, int h, int w, const float* T, int C,
                    const void* labels, int label_bytes, int H, int W, int ignore,

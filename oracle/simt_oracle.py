@@ -78,13 +78,15 @@ def cross_entropy_2d(predict: torch.Tensor, target: torch.Tensor, *, is_softmax:
 # a1-a4 composed: the T-corrected head exactly as the training loop runs it
 # --------------------------------------------------------------------------
 def simt_head_loss(logits_lo: torch.Tensor, T: torch.Tensor, labels: torch.Tensor, out_size,
-                   ignore_label: int = IGNORE_LABEL) -> torch.Tensor:
+                   ignore_label: int = IGNORE_LABEL, ce=None) -> torch.Tensor:
     """loss_y = Tseg_loss(mm(softmax(interp(interp(pred))), T), label).
 
     Reference: tools/trainV2_simt.py:371-372 (first upsample), :402-403 /
     :405-406 (second, same-size upsample; channel softmax; NHWC flatten;
     ``torch.mm`` with T [CK, C]; reshape back to NCHW), :408-409
-    (``CrossEntropy2d(is_softmax=False)``, built at :304).
+    (``CrossEntropy2d(is_softmax=False)``, built at :304).  ``ce``: the reference's own
+    ``CrossEntropy2d(is_softmax=False)`` instance (oracle/_ref/loss.py, see oracle/make_ref.py) to
+    use for :408 instead of the restatement above.
     """
     B, CK = logits_lo.shape[:2]
     H, W = out_size
@@ -93,6 +95,8 @@ def simt_head_loss(logits_lo: torch.Tensor, T: torch.Tensor, labels: torch.Tenso
     p = torch.softmax(upsample_bilinear_ac(up, (H, W)), dim=1)         # :402
     p = p.permute(0, 2, 3, 1).contiguous().view(-1, CK)
     q = torch.mm(p, T).view(B, H, W, C).permute(0, 3, 1, 2)            # :403
+    if ce is not None:
+        return ce(q, labels)                                                          # :408, the reference's class
     return cross_entropy_2d(q, labels, is_softmax=False, ignore_label=ignore_label)  # :408
 
 

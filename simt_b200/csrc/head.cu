@@ -4,6 +4,8 @@
 
 namespace simt {
 
+long long xchg_max_spins();   // xchg.cu
+
 // head_ident.cu: the IDENT = true instantiations
 int dispatch_modes_ident(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out);
 
@@ -20,7 +22,7 @@ __global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlog
                                                          const LabelT* __restrict__ labels, long long npix, int C,
                                                          int ignore, unsigned long long* __restrict__ accum,
                                                          unsigned long long* __restrict__ ticket,
-                                                         double* __restrict__ count_local) {
+                                                         double* __restrict__ count_local, const XchgArgs X) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   // ---- zero dLogits ----
@@ -73,6 +75,16 @@ __global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlog
       *accum = 0ULL;
       *ticket = 0ULL;
       *count_local = (double)total;
+      if (X.world > 1) {
+        // sharded step: this rank's count goes into slot [parity][rank] of EVERY mailbox as one tagged 8-byte word
+        // (peer stores over NVLink; value and step number arrive together, no fence); the main kernel's CTAs pick the
+        // counts up in their prologue
+        unsigned char* own = X.mail[X.rank];
+        const unsigned long long seq = step_seq(own);
+        const int par = (int)(seq & 1ULL);
+        const unsigned long long word = count_word(seq, total);
+        for (int r = 0; r < X.world; ++r) st_relaxed_sys(count_slot_of(X.mail[r], par, X.rank), word);
+      }
     }
   }
 }
@@ -87,9 +99,11 @@ static constexpr int kFinMaxPer = 8;   // tiles per slice held in registers: nti
 __global__ void __launch_bounds__(1024) head_finalize_kernel(
     float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
     int nparts, int ntiles, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
-    double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, const int* __restrict__ err,
-    const float* __restrict__ grad_out, const double* __restrict__ count_dev) {
+    double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, int* __restrict__ err,
+    const float* __restrict__ grad_out, const double* __restrict__ count_dev, unsigned long long* __restrict__ fin_ticket,
+    const XchgArgs X) {
   const int ndt = C * CKP;
+  const bool sharded = X.world > 1;   // loss / dT are final only after the exchange at the end of this kernel
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   __shared__ double sm[kFinSlices][33];
   __shared__ long long smi[kFinSlices];
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
         if (stats) stats[2 + k * C + y] = -t;
         // MODE_STEP on one GPU: grad_out / N_valid is already known on the device (count pass)
         const double sc = count_dev ? (grad_out ? (double)__ldg(grad_out) : 1.0) / *count_dev : (double)gscale;
-        if (dT_out) dT_out[k * C + y] = (float)(-t * sc);
+        if (dT_out && !sharded) dT_out[k * C + y] = (float)(-t * sc);
       }
     }
   } else {
@@ -142,11 +156,80 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
       *counter = 0ULL;  // the main kernel of this call has finished: re-arm the unit scheduler
       const double ls = -kLn2 * l;
       if (stats) { stats[0] = ls; stats[1] = (double)c; }
-      if (loss_mean) {
+      if (loss_mean && !sharded) {
         float m = (float)(ls / (double)c);  // 0/0 -> NaN like the reference's mean over nothing
         if (err && (*err & SIMT_ERRBIT_LABEL_RANGE)) m = nanf("");
         *loss_mean = m;
       }
+    }
+  }
+  if (!sharded) return;
+  // ---- sharded step: all-reduce of `stats` over peer memory ----------------------------------------------------
+  // Every block pushes the stats entries it has just written into slot [parity][rank] of every mailbox as tagged
+  // words (peer stores over NVLink), then polls the same entries of all `world` slots of its OWN mailbox, sums them
+  // in rank order (so the reduced values are bitwise identical on every rank) and writes the final stats / dT / loss.
+  // No block waits for another block; the last one to finish advances the step counter.
+  __shared__ int s_bad;
+  unsigned char* own = X.mail[X.rank];
+  const unsigned long long seq = step_seq(own);
+  const int par = (int)(seq & 1ULL);
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();   // this block's local stats entries are written (and s_bad is initialised)
+  const float poison = nanf("");
+  // the global valid count: the tagged count words the main kernel already waited for
+  double cnt = 0.0;
+  for (int r = 0; r < X.world; ++r) cnt += (double)(ld_relaxed_sys(count_slot_of(own, par, r)) & kCountMask);
+  const double sc = (grad_out ? (double)__ldg(grad_out) : 1.0) / cnt;
+  if ((int)blockIdx.x < (int)gridDim.x - 1) {
+    const int o = blockIdx.x * 32 + tx;
+    const int y = o / CKP, k = o - y * CKP;
+    const bool mine = o < ndt && k < CK;
+    const int i = 2 + k * C + y;
+    if (mine && ty < X.world) ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.n_stats), i, seq, stats[i]);
+    if (mine && ty == 0) {
+      double t = 0.0;
+      bool ok = true;
+      for (int r = 0; r < X.world; ++r) {
+        double v = 0.0;
+        ok = ll_wait_f64(slot_of(own, par, r, X.n_stats), i, seq, X.max_spins, &v) && ok;
+        t += v;
+      }
+      if (!ok) s_bad = 1;
+      stats[i] = ok ? t : (double)poison;
+      if (dT_out) dT_out[i - 2] = ok ? (float)(t * sc) : poison;
+    }
+  } else {
+    if (tid < 2 * X.world) ll_push_f64(slot_of(X.mail[tid >> 1], par, X.rank, X.n_stats), tid & 1, seq, stats[tid & 1]);
+    __syncthreads();
+    if (tid == 0) {
+      double t[2] = {0.0, 0.0};
+      bool ok = true;
+      for (int i = 0; i < 2; ++i)
+        for (int r = 0; r < X.world; ++r) {
+          double v = 0.0;
+          ok = ll_wait_f64(slot_of(own, par, r, X.n_stats), i, seq, X.max_spins, &v) && ok;
+          t[i] += v;
+        }
+      if (!ok) s_bad = 1;
+      stats[0] = ok ? t[0] : (double)poison;
+      stats[1] = ok ? t[1] : (double)poison;
+      if (loss_mean) {
+        float m = (float)(t[0] / t[1]);   // 0/0 -> NaN like the reference's mean over nothing
+        if (!ok || (err && (*err & SIMT_ERRBIT_LABEL_RANGE))) m = poison;
+        *loss_mean = m;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_bad && err) atomicOr(err, SIMT_ERRBIT_XCHG_TIMEOUT);
+    __threadfence();
+    const unsigned long long t = atomicAdd(fin_ticket, 1ULL);
+    if (t == (unsigned long long)gridDim.x - 1ULL) {   // every block is done with this step's slots
+      *fin_ticket = 0ULL;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long*>(own) = seq;   // the step is over: advance the counter
     }
   }
 }
@@ -293,7 +376,8 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
   head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, mode, gscale,
-                                              A.counter, stats, loss_mean, dT_out, err_flag, nullptr, nullptr);
+                                              A.counter, stats, loss_mean, dT_out, err_flag, nullptr, nullptr, nullptr,
+                                              XchgArgs{});
   return (int)cudaGetLastError();
 }
 
@@ -302,7 +386,7 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
 static int run_step(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
                     int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
                     double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes,
-                    cudaStream_t st) {
+                    const XchgArgs& X, cudaStream_t st) {
   int rc = validate(logits, B, CK, h, w, C, labels, label_bytes, H, W, T);
   if (rc) return rc;
   if (!err_flag || !workspace || !dlogits || !stats) return SIMT_EINVAL;
@@ -312,6 +396,7 @@ static int run_step(const float* logits, int B, int CK, int h, int w, const floa
   A.logits = logits; A.T = T; A.labels = labels;
   A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = ignore;
   A.gscale = 1.f; A.dlogits = dlogits; A.err = err_flag; A.grad_out = grad_out;
+  A.X = X;
   A.label_words_ok = (label_bytes == 1 && (reinterpret_cast<uintptr_t>(labels) & 3) == 0 &&
                       (((long long)B * H * W) & 3) == 0) ? 1 : 0;
   rc = make_plan(MODE_STEP, B, CK, C, h, w, H, W, &A, &P);
@@ -325,6 +410,7 @@ static int run_step(const float* logits, int B, int CK, int h, int w, const floa
   unsigned long long* accum = reinterpret_cast<unsigned long long*>(ws + 8);     // the 64-byte header has room
   unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws + 16);
   double* count_local = reinterpret_cast<double*>(ws + 24);
+  unsigned long long* fin_ticket = reinterpret_cast<unsigned long long*>(ws + 32);
   A.count_local = count_local;
   A.part_loss = reinterpret_cast<double*>(ws + 64);
   A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
@@ -334,17 +420,18 @@ static int run_step(const float* logits, int B, int CK, int h, int w, const floa
   const int pgrid = di.sm_count * 4;
   if (label_bytes == 1)
     head_prep_kernel<uint8_t><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const uint8_t*>(labels), npix, C, ignore,
-                                                     accum, ticket, count_local);
+                                                     accum, ticket, count_local, X);
   else
     head_prep_kernel<long long><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const long long*>(labels), npix, C,
-                                                       ignore, accum, ticket, count_local);
+                                                       ignore, accum, ticket, count_local, X);
   SIMT_CUDA_TRY(cudaGetLastError());
   int grid = 0;
   rc = dispatch_all(MODE_STEP, label_bytes, A, P, st, &grid);
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
   head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, MODE_STEP,
-                                              1.f, A.counter, stats, loss_mean, dT, err_flag, grad_out, count_local);
+                                              1.f, A.counter, stats, loss_mean, dT, err_flag, grad_out, count_local,
+                                              fin_ticket, X);
   return (int)cudaGetLastError();
 }
 
@@ -379,7 +466,8 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
   if (rc) return rc;
   // one block: loss / count partials and the scheduler re-arm (there are no dT tiles in this mode)
   head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, 0, CK, P.CKP, C, MODE_PLACE, 1.f,
-                                           A.counter, stats, loss_mean, nullptr, nullptr, nullptr, nullptr);
+                                           A.counter, stats, loss_mean, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                           XchgArgs{});
   return (int)cudaGetLastError();
 }
 
@@ -429,7 +517,23 @@ int simt_head_step(const float* logits, int B, int CK, int h, int w, const float
                    int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
                    double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes, void* stream) {
   return run_step(logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, grad_out, dlogits, dT, stats, loss_mean,
-                  err_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+                  err_flag, workspace, workspace_bytes, XchgArgs{}, (cudaStream_t)stream);
+}
+
+int simt_head_step_sharded(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
+                           int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
+                           double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes,
+                           int rank, int world, void* const* mailboxes, void* stream) {
+  if (!mailboxes || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return SIMT_EINVAL;
+  XchgArgs X{};
+  for (int r = 0; r < world; ++r) {
+    if (!mailboxes[r]) return SIMT_EINVAL;
+    X.mail[r] = static_cast<unsigned char*>(mailboxes[r]);
+  }
+  X.rank = rank; X.world = world; X.n_stats = 2 + CK * C;
+  X.max_spins = xchg_max_spins();
+  return run_step(logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, grad_out, dlogits, dT, stats, loss_mean,
+                  err_flag, workspace, workspace_bytes, X, (cudaStream_t)stream);
 }
 
 int simt_placeholder_fwdbwd(const float* logits, int B, int CK, int h, int w, int C, int H, int W, float thres,

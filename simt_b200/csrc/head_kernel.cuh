@@ -44,7 +44,7 @@
 #include <mutex>
 #include <type_traits>
 #pragma once
-#include "common.cuh"
+#include "xchg.cuh"
 
 namespace simt {
 
@@ -80,6 +80,9 @@ struct HeadArgs {
   // MODE_STEP: upstream gradient (device scalar or null = 1) and the valid-pixel count written by head_prep_kernel
   const float* grad_out;
   const double* count_local;
+  // MODE_STEP, batch sharded over several GPUs: the GLOBAL valid-pixel count is the sum of the ranks' counts, which
+  // head_prep_kernel pushes into every peer's mailbox; every CTA acquires them in its prologue
+  XchgArgs X;
 };
 
 template <typename LabelT>
@@ -230,6 +233,23 @@ struct LabelFetch<long long> {
   }
 };
 
+// Sharded step: wait (bounded) for every rank's valid-pixel count in this rank's mailbox and return
+// grad_out / sum(counts); NaN + SIMT_ERRBIT_XCHG_TIMEOUT when a peer never arrives.  One thread per CTA, in the prologue.
+static __device__ __forceinline__ float acquire_global_scale(const XchgArgs& X, const float* grad_out, int* err) {
+  unsigned char* own = X.mail[X.rank];
+  const unsigned long long seq = step_seq(own);
+  const int par = (int)(seq & 1ULL);
+  double c = 0.0;
+  bool ok = true;
+  for (int r = 0; r < X.world; ++r) {   // the counts are integers, any order is exact
+    unsigned long long n = 0ULL;
+    ok = wait_count(count_slot_of(own, par, r), seq, X.max_spins, &n) && ok;
+    c += (double)n;
+  }
+  if (!ok && err) atomicOr(err, SIMT_ERRBIT_XCHG_TIMEOUT);
+  return ok ? (float)((grad_out ? (double)__ldg(grad_out) : 1.0) / c) : nanf("");
+}
+
 static constexpr int kEdgeRows = 16;  // pixel rows per cell-row whose edge column is staged in smem
 
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB, bool IDENT>
@@ -283,7 +303,10 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
     Ts[i] = -v;
   }
   if (MODE == MODE_STEP && tid == 0)   // the valid-pixel count was produced by head_prep_kernel before this launch
-    s_gs = (float)((A.grad_out ? (double)__ldg(A.grad_out) : 1.0) / *A.count_local);
+    // (sharded step: the GLOBAL count = the sum of the ranks' counts, pushed into this rank's mailbox by the peers'
+    // head_prep_kernel; a peer that never arrives poisons the gradients with NaN, never a partial sum)
+    s_gs = (A.X.world > 1) ? acquire_global_scale(A.X, A.grad_out, A.err)
+                           : (float)((A.grad_out ? (double)__ldg(A.grad_out) : 1.0) / *A.count_local);
   for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
   for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
 #ifdef SIMT_EXP_LXTAB
@@ -337,6 +360,8 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
       D2[q] = make_float2(0.f, 0.f);
     }
   };
+
+  auto grad_scale = [&]() -> float { return (MODE == MODE_BWD) ? A.gscale : (MODE == MODE_STEP ? s_gs : 1.f); };
 
   long long unit = claim_get(claim_raw());
 #ifdef SIMT_EXP_PREFETCH
@@ -739,6 +764,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           }
           // right edge of the unit: node column edge_gx belongs to the next unit (or is the image's
           // last column).  Its per-row values wait in the warp's smem slice until the cell-row is done.
+          const float gs = edge_smem ? 0.f : grad_scale();   // (warp-uniform call site)
           if (edge_smem) {
             if (last_cell) {
               float* er = Ew + (Y - Y0) * (CKP + 1) + kbase;
@@ -748,7 +774,6 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
             }
           } else if (last_cell) {
             float* dst = A.dlogits + ((size_t)b * CK + kbase) * h * w;
-            const float gs = (MODE == MODE_BWD) ? A.gscale : (MODE == MODE_STEP ? s_gs : 1.f);
             const float w0y = (1.f - ly) * gs, w1y = ly * gs;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
@@ -765,7 +790,7 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 
       if (BWD) {
         float* dst = A.dlogits + (size_t)b * CK * h * w;
-        const float gs = (MODE == MODE_BWD) ? A.gscale : (MODE == MODE_STEP ? s_gs : 1.f);
+        const float gs = grad_scale();
         if (cell_ok) {
           const unsigned plane = (unsigned)(h * w);
           float* d0 = dst + (size_t)kbase * plane + (gy0 * w + gx0);

@@ -8,8 +8,8 @@ and ONE int64 all-reduce of the confusion matrix at the end of an evaluation.  d
 NVLink on the GPU box, gloo in the CPU tests of this host logic.
 
 On one node the per-step exchange does not go through a library collective at all: ``PeerMailbox`` sets up CUDA-IPC
-mapped mailboxes between the ranks and the scale kernel exchanges the stats itself over NVLink peer stores
-(csrc/xchg.cu, ``simt_head_scale_sharded``); torch.distributed only carries the 64-byte handles once.
+mapped mailboxes between the ranks and the step's own kernels exchange the valid counts and the stats over NVLink peer
+stores (csrc/xchg.cu, ``simt_head_step_sharded``); torch.distributed only carries the 64-byte handles once.
 """
 from __future__ import annotations
 
@@ -60,7 +60,7 @@ class PeerMailbox:
 
     Collective constructor: every rank of ``group`` (all on ONE node, <= 8) creates its mailbox, the 64-byte IPC
     handles are all-gathered and every peer's mailbox is opened.  ``ptrs`` is the ctypes array
-    ``simt_head_scale_sharded`` takes.  Raises ``RuntimeError`` when peer mapping is not possible (other node, no
+    ``simt_head_step_sharded`` takes.  Raises ``RuntimeError`` when peer mapping is not possible (other node, no
     P2P); callers fall back to ``reduce_head_stats`` (a library all-reduce).
     """
 
@@ -106,10 +106,19 @@ class PeerMailbox:
         self.ptrs = ptrs
 
     def close(self):
+        """Unmap the peers' mailboxes and free this rank's.  Peers that keep stepping afterwards wait for this rank
+        until their bound expires (simt_xchg_set_timeout), so close after the last step on every rank."""
         with torch.cuda.device(self.dev):
+            torch.cuda.synchronize(self.dev)
             for p in self.peers.values():
                 self.lib.simt_xchg_close(p)
             self.peers = {}
             if self.own:
                 self.lib.simt_xchg_destroy(self.own)
                 self.own = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

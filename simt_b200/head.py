@@ -61,7 +61,8 @@ def check_errors(dev=None) -> None:
         if v & 2:
             what.append("n_cols*a+b outside the histogram table")
         if v & 4:
-            what.append("sharded scale: a peer rank's stats never arrived (bounded wait expired)")
+            what.append("sharded step: a peer rank's count / stats never arrived (bounded wait expired; this rank's "
+                        "loss, dT and possibly dlogits of that step are NaN)")
         raise IndexError("simt_b200: " + "; ".join(what))
 
 
@@ -98,8 +99,9 @@ def head_forward_raw(logits, T, labels, out_size, ignore=255, need_grad=True):
     B, CK, h, w = logits.shape
     C = CK if Tc is None else Tc.size(1)
     dev = logits.device
-    nws = lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W)
-    ws = _workspace(dev, nws)
+    with torch.cuda.device(dev):             # the workspace is sized from this device's SM count
+        nws = lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W)
+        ws = _workspace(dev, nws)
     stats = torch.empty(2 + CK * C, dtype=torch.float64, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     err = error_flag(dev)
@@ -199,11 +201,12 @@ class SimTHead(torch.nn.Module):
 class HeadRunner:
     """Static-shape, allocation-free form of the fused head for training loops and benchmarks.
 
-    All outputs are preallocated once; ``step`` enqueues, on one GPU, a label-count + zeroing pass, the fused
-    fwd/bwd kernel (which applies grad_out / N_valid itself) and finalize; sharded (``group``), memset + fused
-    kernel + finalize + a scale kernel that exchanges the 2.9 KB stats buffer with its peers first.  It returns views
+    All outputs are preallocated once; ``step`` enqueues a label-count + zeroing pass, the fused fwd/bwd kernel (which
+    applies grad_out / N_valid itself) and finalize.  Sharded (``group``) the same three kernels also exchange the
+    valid counts and the 2.9 KB stats buffer with their peers over CUDA-IPC peer memory (``simt_head_step_sharded``),
+    so the mean is over the GLOBAL batch and dT is summed over ranks.  It returns views
     (loss f32[], dlogits f32[B,CK,h,w], dT f32[CK,C]) without synchronising.  ``graph_step`` is the same work
-    replayed from a CUDA graph.
+    replayed from a CUDA graph.  ``close()`` releases the peer mailboxes (also a context manager).
     """
 
     def __init__(self, B, CK, C, h, w, H, W, device=None, ignore=255, label_dtype=torch.uint8, group=None,
@@ -211,11 +214,16 @@ class HeadRunner:
         self.lib = _lib.load()
         self.shape = (int(B), int(CK), int(C), int(h), int(w), int(H), int(W))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.ignore = int(ignore)
+        self.label_dtype = label_dtype
         self.label_bytes = 1 if label_dtype == torch.uint8 else 8
         self.group = group
         B, CK, C, h, w, H, W = self.shape
-        self.ws = torch.zeros(self.lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W), dtype=torch.uint8, device=self.dev)
+        with torch.cuda.device(self.dev):       # the workspace is sized from this device's SM count
+            nws = self.lib.simt_head_workspace_bytes(B, CK, C, h, w, H, W)
+        self.ws = torch.zeros(nws, dtype=torch.uint8, device=self.dev)
         self.stats = torch.zeros(2 + CK * C, dtype=torch.float64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.dlogits = torch.zeros(B, CK, h, w, dtype=torch.float32, device=self.dev)
@@ -225,23 +233,74 @@ class HeadRunner:
                    self.dlogits.data_ptr(), self.dT.data_ptr(), self.err.data_ptr())
         self._graphs = {}
         self._graph_keepalive = []
-        # sharded: the stats exchange is fused into the scale kernel over CUDA-IPC peer memory when every rank can
-        # map every other rank's mailbox (one node); otherwise one library all-reduce per step
+        self._checked = set()
+        # sharded: the exchanges are fused into the step's kernels over CUDA-IPC peer memory when every rank can map
+        # every other rank's mailbox (one node); otherwise one library all-reduce per step
         self.mailbox = None
         self._world = 1
         if group is not None:
             import torch.distributed as dist
             self._world = dist.get_world_size(group)
-        if group is not None and exchange == "p2p":
-            import torch.distributed as dist
-            if dist.get_world_size(group) > 1:
-                from .dist import PeerMailbox
-                try:
-                    self.mailbox = PeerMailbox(2 + CK * C, group, self.dev)
-                except RuntimeError:
-                    self.mailbox = None
+        if group is not None and exchange == "p2p" and self._world > 1:
+            from .dist import PeerMailbox
+            try:
+                self.mailbox = PeerMailbox(2 + CK * C, group, self.dev)
+            except RuntimeError:
+                self.mailbox = None
+
+    # ---- lifetime ----------------------------------------------------------------------------------------------
+    def close(self):
+        """Release the peer mailboxes (collective in spirit: peers that keep stepping would wait for this rank)."""
+        self._graphs.clear()
+        self._graph_keepalive.clear()
+        if self.mailbox is not None:
+            self.mailbox.close()
+            self.mailbox = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- argument checks (first call per buffer set; the kernels take raw pointers) -------------------------------
+    def _check(self, logits, T, labels, grad_out=None):
+        key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
+               None if grad_out is None else grad_out.data_ptr())
+        if key in self._checked:
+            return
+        B, CK, C, h, w, H, W = self.shape
+
+        def bad(what):
+            raise ValueError(f"HeadRunner{self.shape}: {what}")
+        if tuple(logits.shape) != (B, CK, h, w) or logits.dtype != torch.float32:
+            bad(f"logits must be float32 [{B}, {CK}, {h}, {w}], got {logits.dtype} {tuple(logits.shape)}")
+        if tuple(labels.shape) != (B, H, W) or labels.dtype != self.label_dtype:
+            bad(f"labels must be {self.label_dtype} [{B}, {H}, {W}], got {labels.dtype} {tuple(labels.shape)}")
+        if T is not None and (tuple(T.shape) != (CK, C) or T.dtype != torch.float32):
+            bad(f"T must be float32 [{CK}, {C}], got {T.dtype} {tuple(T.shape)}")
+        if T is None and CK != C:
+            bad("T=None (plain CE) needs CK == C")
+        for name, t in (("logits", logits), ("labels", labels), ("T", T), ("grad_out", grad_out)):
+            if t is None:
+                continue
+            if not t.is_contiguous():
+                bad(f"{name} must be contiguous")
+            if t.device != self.dev:
+                bad(f"{name} is on {t.device}, the runner on {self.dev}")
+        if grad_out is not None and (grad_out.numel() != 1 or grad_out.dtype != torch.float32):
+            bad("grad_out must be a float32 scalar tensor")
+        if len(self._checked) < 64:
+            self._checked.add(key)
 
     def fwdbwd(self, logits, T, labels, stream=None):
+        self._check(logits, T, labels)
         B, CK, C, h, w, H, W = self.shape
         ws, nws, stats, loss, dl, _, err = self._p
         rc = self.lib.simt_head_fwdbwd(logits.data_ptr(), B, CK, h, w, None if T is None else T.data_ptr(), C,
@@ -259,50 +318,45 @@ class HeadRunner:
         if rc:
             _lib.check(rc, "simt_head_scale")
 
-    def scale_sharded(self, grad_out=None, stream=None):
-        """scale with the cross-rank stats exchange fused in (``simt_head_scale_sharded``); collective."""
-        B, CK, C, h, w, H, W = self.shape
-        _, _, stats, loss, dl, dT, err = self._p
-        mb = self.mailbox
-        rc = self.lib.simt_head_scale_sharded(dl, B * CK * h * w, stats, CK, C,
-                                              None if grad_out is None else grad_out.data_ptr(), dT, loss,
-                                              mb.rank, mb.world, mb.ptrs, err,
-                                              _stream_ptr() if stream is None else stream)
-        if rc:
-            _lib.check(rc, "simt_head_scale_sharded")
-
     def step(self, logits, T, labels, grad_out=None):
         """One training step: (loss, dlogits, dT), final and global, without synchronising.
         One GPU: ``simt_head_step`` (label count + zeroing, fused kernel applying grad_out / N itself, finalize).
-        Sharded: fwdbwd, then the scale kernel with the stats exchange fused in over the peer mailboxes (ONE
-        rendezvous per step), or -- fallback -- one NCCL all-reduce between fwdbwd and scale."""
+        Sharded: ``simt_head_step_sharded`` -- the same three kernels exchange counts and stats over the peer
+        mailboxes -- or, when the peers cannot be mapped, fwdbwd + one NCCL all-reduce + scale."""
+        self._check(logits, T, labels, grad_out)
         stream = _stream_ptr()
-        if self._world > 1:
-            self.fwdbwd(logits, T, labels, stream)
-            if self.mailbox is not None:
-                self.scale_sharded(grad_out, stream)     # loss / stats / dT are global on return
-            else:
-                import torch.distributed as dist
-                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
-                self.scale(grad_out, stream)
-            return self.loss, self.dlogits, self.dT
         B, CK, C, h, w, H, W = self.shape
         ws, nws, stats, loss, dl, dT, err = self._p
-        rc = self.lib.simt_head_step(logits.data_ptr(), B, CK, h, w, None if T is None else T.data_ptr(), C,
-                                     labels.data_ptr(), self.label_bytes, H, W, self.ignore,
-                                     None if grad_out is None else grad_out.data_ptr(), dl, dT, stats, loss, err, ws, nws,
-                                     stream)
+        tp = None if T is None else T.data_ptr()
+        gp = None if grad_out is None else grad_out.data_ptr()
+        with torch.cuda.device(self.dev):
+            if self._world > 1 and self.mailbox is None:
+                import torch.distributed as dist
+                self.fwdbwd(logits, T, labels, stream)
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+                self.scale(grad_out, stream)
+                self.loss.copy_((self.stats[0] / self.stats[1]).to(torch.float32))   # the GLOBAL mean, as on the p2p path
+                return self.loss, self.dlogits, self.dT
+            if self._world > 1:
+                mb = self.mailbox
+                rc = self.lib.simt_head_step_sharded(logits.data_ptr(), B, CK, h, w, tp, C, labels.data_ptr(),
+                                                     self.label_bytes, H, W, self.ignore, gp, dl, dT, stats, loss, err,
+                                                     ws, nws, mb.rank, mb.world, mb.ptrs, stream)
+                what = "simt_head_step_sharded"
+            else:
+                rc = self.lib.simt_head_step(logits.data_ptr(), B, CK, h, w, tp, C, labels.data_ptr(), self.label_bytes,
+                                             H, W, self.ignore, gp, dl, dT, stats, loss, err, ws, nws, stream)
+                what = "simt_head_step"
         if rc:
-            _lib.check(rc, "simt_head_step")
+            _lib.check(rc, what)
         return self.loss, self.dlogits, self.dT
 
     def graph_step(self, logits, T, labels, grad_out=None):
-        """``step`` replayed from a CUDA graph: its three (one GPU) or four (sharded) launches are captured ONCE for this
-        exact set of buffers (keyed by their addresses) and re-launched as one graph afterwards -- they are
-        launch-latency-bound next to a 90 us kernel.  The graph reads the buffers' CURRENT contents on every
-        replay (refill ``logits`` / ``labels`` / ``T`` in place).  Sharded runs replay too when the stats exchange is
-        the fused peer-memory one (no library collective inside the graph); with the all-reduce fallback they take the
-        eager path."""
+        """``step`` replayed from a CUDA graph: its three launches are captured ONCE for this exact set of buffers
+        (keyed by their addresses) and re-launched as one graph afterwards -- they are launch-latency-bound next to a
+        90 us kernel.  The graph reads the buffers' CURRENT contents on every replay (refill ``logits`` / ``labels``
+        / ``T`` in place).  Sharded runs replay too when the exchange is the fused peer-memory one (no library
+        collective inside the graph); with the all-reduce fallback they take the eager path."""
         if self._world > 1 and self.mailbox is None:
             return self.step(logits, T, labels, grad_out)
         key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
@@ -329,28 +383,41 @@ class HeadRunner:
 class HostPrefetcher:
     """Double-buffered pinned-host -> device uploader for (logits, labels) batches.
 
-    ``submit(logits_host, labels_host)`` enqueues the copies of the NEXT batch on a side stream;
-    ``get()`` makes the compute stream wait for them and returns the device tensors.  While a step
-    computes, the next step's 9 MB of inputs cross PCIe -- the usual input pipeline of a training loop.
+    A batch travels as ONE packed buffer (logits bytes, then label bytes): ``host_buffer()`` hands out pinned staging
+    buffers with ``.logits`` / ``.labels`` views to fill, ``submit(buf)`` enqueues ONE copy of the next batch on a side
+    stream, ``get()`` makes the compute stream wait for it and returns the device views.  While a step computes, the
+    next step's 9 MB of inputs cross PCIe -- the usual input pipeline of a training loop.
     """
+
+    class _Packed:
+        def __init__(self, raw, B, CK, h, w, H, W, label_dtype):
+            nl = B * CK * h * w * 4
+            off = (nl + 15) // 16 * 16           # labels start 16-byte aligned
+            self.raw = raw
+            self.logits = raw[:nl].view(torch.float32).view(B, CK, h, w)
+            self.labels = raw[off:].view(label_dtype).view(B, H, W)
 
     def __init__(self, B, CK, h, w, H, W, device=None, label_dtype=torch.uint8):
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.shape = (B, CK, h, w, H, W, label_dtype)
+        self.nbytes = (B * CK * h * w * 4 + 15) // 16 * 16 + B * H * W * torch.empty((), dtype=label_dtype).element_size()
         self.stream = torch.cuda.Stream(device=self.dev)
-        self.bufs = [(torch.empty(B, CK, h, w, dtype=torch.float32, device=self.dev),
-                      torch.empty(B, H, W, dtype=label_dtype, device=self.dev)) for _ in range(2)]
+        self.bufs = [self._Packed(torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev), *self.shape)
+                     for _ in range(2)]
         self.events = [torch.cuda.Event(), torch.cuda.Event()]
         self.free = [torch.cuda.Event(), torch.cuda.Event()]
         self.slot = 0
         self.pending = None
 
-    def submit(self, logits_host: torch.Tensor, labels_host: torch.Tensor) -> None:
+    def host_buffer(self):
+        """A pinned staging buffer (fill ``.logits`` / ``.labels``, then ``submit`` it)."""
+        return self._Packed(torch.empty(self.nbytes, dtype=torch.uint8).pin_memory(), *self.shape)
+
+    def submit(self, host_buf) -> None:
         slot = self.slot
-        lg, lab = self.bufs[slot]
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.free[slot])          # the compute that last used this slot is done
-            lg.copy_(logits_host, non_blocking=True)
-            lab.copy_(labels_host, non_blocking=True)
+            self.bufs[slot].raw.copy_(host_buf.raw, non_blocking=True)
             self.events[slot].record(self.stream)
         self.pending = slot
         self.slot ^= 1
@@ -358,10 +425,10 @@ class HostPrefetcher:
     def get(self):
         slot = self.pending
         torch.cuda.current_stream(self.dev).wait_event(self.events[slot])
-        return self.bufs[slot]
+        return self.bufs[slot].logits, self.bufs[slot].labels
 
     def release(self, slot_tensors) -> None:
         """Call after the step that consumed ``slot_tensors`` has been enqueued."""
         for i, b in enumerate(self.bufs):
-            if b[0] is slot_tensors[0]:
+            if b.logits is slot_tensors[0]:
                 self.free[i].record(torch.cuda.current_stream(self.dev))

@@ -283,19 +283,22 @@ def test_host_prefetcher_double_buffering_delivers_every_batch():
     dev = torch.device("cuda")
     B, CK, h, w, H, W = 2, 19, 9, 17, 64, 128
     T = O.sig_ntm_forward(torch.randn(CK, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, 0)
-    host = []
+    pre = simt_b200.HostPrefetcher(B, CK, h, w, H, W, device=dev)
+    host, packed = [], []
     for i in range(5):
         lg, lab = O.synth_head_inputs(B, CK, h, w, H, W, seed=70 + i, coherent=True, ignore_frac=0.1)
-        host.append((lg.pin_memory(), lab.to(torch.uint8).pin_memory()))
-    pre = simt_b200.HostPrefetcher(B, CK, h, w, H, W, device=dev)
+        host.append((lg, lab.to(torch.uint8)))
+        buf = pre.host_buffer()                  # one pinned buffer per batch: logits bytes, then label bytes
+        buf.logits.copy_(lg); buf.labels.copy_(lab.to(torch.uint8))
+        packed.append(buf)
     runner = simt_b200.HeadRunner(B, CK, 19, h, w, H, W, device=dev)
     Td = T.to(dev)
     losses = []
-    pre.submit(*host[0])
+    pre.submit(packed[0])
     for i in range(5):
         cur = pre.get()
         if i + 1 < 5:
-            pre.submit(*host[i + 1])
+            pre.submit(packed[i + 1])
         loss, _, _ = runner.step(cur[0], Td, cur[1])
         pre.release(cur)
         losses.append(loss.clone())
