@@ -44,6 +44,7 @@ enum {
 #define SIMT_ERRBIT_LABEL_RANGE 1 /* head: label not ignore and not in [0, C)        */
 #define SIMT_ERRBIT_PRED_RANGE  2 /* histograms: n_cols*a+b outside [0, rows*cols)   */
 #define SIMT_ERRBIT_XCHG_TIMEOUT 4 /* sharded step: a peer's count / stats never arrived  */
+#define SIMT_ERRBIT_NEXT_LABELS  8 /* sharded step: labels differ from the next_labels announced one step earlier */
 
 int         simt_b200_abi_version(void);
 const char* simt_b200_strerror(int code);
@@ -191,7 +192,7 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
  * peer memory (NVLink / NVSwitch P2P stores into CUDA-IPC mapped mailboxes) from inside the step's
  * own kernels -- no library collective, no extra launch, no pass over dLogits.
  *
- * simt_xchg_create: cudaMalloc + zero a mailbox of simt_xchg_bytes(2 + CK*C) bytes on the current
+ * simt_xchg_create: cudaMalloc + zero a mailbox of simt_xchg_bytes(C) bytes on the current
  *   device and export its 64-byte CUDA IPC handle.  The caller exchanges the handles (any
  *   transport: torch.distributed all-gather, MPI, a pipe) and opens every peer's mailbox with
  *   simt_xchg_open (current device = the opener's GPU).  close / destroy undo open / create.
@@ -206,13 +207,19 @@ int simt_bilinear_gather(const float* src, int B, int C, int h, int w, int H, in
  *   mailboxes: HOST array [world] of device pointers, mailboxes[rank] = this rank's own.
  *   Every rank must call it once per step, in the same order.  No host-side step argument: the
  *   call sequence can be captured in a CUDA graph.
- * simt_xchg_set_timeout: bound of every in-kernel wait, in polls of ~64 ns (default 2^28, about
- *   half a minute; <= 0 waits for ever).  A peer that does not arrive in time poisons this rank's
+ *   Pipelined form (no rank ever waits inside a step): `next_labels` (same dtype / shape as labels, or
+ *   NULL) are the labels the NEXT call will be given -- their count is exchanged now, one step early
+ *   (a next call with other labels sets SIMT_ERRBIT_NEXT_LABELS); `defer` != 0 only pushes this
+ *   step's stats: loss_mean / dT / stats become final in the prologue of the next call on the same
+ *   workspace + mailboxes, or in simt_head_finish_sharded (same output pointers), by which time the
+ *   peers' words have long arrived.  dlogits are always final on return (stream order).
+ * simt_xchg_set_timeout: bound of every in-kernel wait, in polls of ~1 us (default 2^24, of the
+ *   order of 10-20 s; <= 0 waits for ever).  A peer that does not arrive in time poisons this rank's
  *   loss_mean, dT, stats (and, when the count is missing, dlogits) with NaN and sets
  *   SIMT_ERRBIT_XCHG_TIMEOUT in err_flag: a rank never continues with a partial sum.  Ranks must
  *   not drift further apart than the bound (raise it around checkpoints / evaluation on one rank).
  * ------------------------------------------------------------------------- */
-size_t simt_xchg_bytes(int n_stats);
+size_t simt_xchg_bytes(int C);
 int simt_xchg_create(size_t bytes, void** mailbox, unsigned char* handle64);
 int simt_xchg_open(const unsigned char* handle64, void** peer_mailbox);
 int simt_xchg_close(void* peer_mailbox);
@@ -222,7 +229,11 @@ int simt_head_step_sharded(const float* logits, int B, int CK, int h, int w, con
                            const void* labels, int label_bytes, int H, int W, int ignore,
                            const float* grad_out, float* dlogits, float* dT, double* stats, float* loss_mean,
                            int* err_flag, void* workspace, size_t workspace_bytes,
-                           int rank, int world, void* const* mailboxes, void* stream);
+                           int rank, int world, void* const* mailboxes,
+                           const void* next_labels, int defer, void* stream);
+int simt_head_finish_sharded(int CK, int C, const float* grad_out, float* dT, double* stats, float* loss_mean,
+                             int* err_flag, void* workspace, size_t workspace_bytes,
+                             int rank, int world, void* const* mailboxes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * simt_head_step: one whole training step of the head on ONE GPU, the form a training loop calls every

@@ -46,7 +46,9 @@ SIGNATURES = {
     "simt_xchg_set_timeout": (None, [c_longlong]),
     "simt_head_step_sharded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                        c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                       c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+                                       c_int, c_int, ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p]),
+    "simt_head_finish_sharded": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "simt_head_step": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "simt_placeholder_fwdbwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,

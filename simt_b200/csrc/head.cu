@@ -1,10 +1,15 @@
 // Host side of the fused SimT head (entry points, plans, the small kernels around the fused one).  The fused kernel
 // itself is in head_kernel.cuh; its T = NULL (plain CE) instantiations are compiled in head_ident.cu.
+#include <cstdlib>
 #include "head_kernel.cuh"
 
 namespace simt {
 
 long long xchg_max_spins();   // xchg.cu
+
+// workspace: [header kWsHeader][staging: 2 + CK*C doubles (sharded, deferred mode: local stats awaiting their push)]
+//            [part_loss f64 x G][part_cnt i64 x G][part_dT f32 x ntiles*C*CKP (sized for G tiles)]
+static size_t ws_staging_bytes(int CK, int C) { return (((size_t)(2 + (size_t)CK * C) * 8) + 127) / 128 * 128; }
 
 // head_ident.cu: the IDENT = true instantiations
 int dispatch_modes_ident(int mode, int label_bytes, const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out);
@@ -14,23 +19,12 @@ static int dispatch_all(int mode, int label_bytes, const HeadArgs& A, const Plan
   return dispatch_modes<false>(mode, label_bytes, A, P, st, grid_out);
 }
 
-// Step prologue (MODE_STEP): zero dLogits and count this rank's valid pixels in ONE pass over the labels, so that the
-// main kernel can apply grad_out / N_valid itself.  The last block to finish publishes the count in `count_local`.
-// Validity is the main kernel's rule exactly: a class id below C that is not the ignore label.
+// (workspace header words WS_*: head_kernel.cuh)
+
+// valid = a class id below C that is not the ignore label (the main kernel's rule exactly)
 template <typename LabelT>
-__global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlogits, long long n_dl,
-                                                         const LabelT* __restrict__ labels, long long npix, int C,
-                                                         int ignore, unsigned long long* __restrict__ accum,
-                                                         unsigned long long* __restrict__ ticket,
-                                                         double* __restrict__ count_local, const XchgArgs X) {
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  // ---- zero dLogits ----
-  const long long n4 = ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) ? (n_dl >> 2) : 0;
-  float4* d4 = reinterpret_cast<float4*>(dlogits);
-  for (long long i = i0; i < n4; i += stride) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long i = n4 * 4 + i0; i < n_dl; i += stride) dlogits[i] = 0.f;
-  // ---- count valid labels ----
+__device__ __forceinline__ unsigned long long count_valid(const LabelT* __restrict__ labels, long long npix, int C,
+                                                          int ignore, long long i0, long long stride) {
   unsigned long long cnt = 0;
   if (sizeof(LabelT) == 1) {
     const int ign8 = (ignore >= 0 && ignore <= 255) ? ignore : 256;
@@ -59,32 +53,97 @@ __global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlog
       cnt += (unsigned)((y >= 0) & (y < (long long)C) & (y != (long long)ignore));
     }
   }
+  return cnt;
+}
+
+// Step prologue (MODE_STEP): zero dLogits and count this rank's valid pixels in ONE pass over the labels, so that the
+// main kernel can apply grad_out / N_valid itself.  The last block to finish publishes the count.
+// Sharded step, additionally:
+//   * the last block pushes this rank's count for this step into every mailbox as one tagged word -- unless the
+//     previous step already did (`next_labels`), in which case it only checks that the labels are the announced ones;
+//   * with `next_labels` it also counts the NEXT step's labels; the fused kernel pushes that count one step early, so
+//     that no rank ever waits for a count.
+template <typename LabelT>
+__global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlogits, long long n_dl,
+                                                         const LabelT* __restrict__ labels,
+                                                         const LabelT* __restrict__ next_labels, long long npix, int C,
+                                                         int ignore, unsigned long long* __restrict__ ws,
+                                                         const XchgArgs X, const FinishArgs F) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // ---- zero dLogits ----
+  const long long n4 = ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) ? (n_dl >> 2) : 0;
+  float4* d4 = reinterpret_cast<float4*>(dlogits);
+  for (long long i = i0; i < n4; i += stride) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = n4 * 4 + i0; i < n_dl; i += stride) dlogits[i] = 0.f;
+  // ---- count valid labels (of this step and, when announced, of the next) ----
+  unsigned long long cnt = count_valid<LabelT>(labels, npix, C, ignore, i0, stride);
+  unsigned long long cnt2 = next_labels ? count_valid<LabelT>(next_labels, npix, C, ignore, i0, stride) : 0ULL;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  __shared__ unsigned long long s_w[8];
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    cnt2 += __shfl_xor_sync(0xffffffffu, cnt2, o);
+  }
+  __shared__ unsigned long long s_w[8], s_w2[8];
+  if ((threadIdx.x & 31) == 0) { s_w[threadIdx.x >> 5] = cnt; s_w2[threadIdx.x >> 5] = cnt2; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long b = 0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) b += s_w[k];
-    atomicAdd(accum, b);
+    unsigned long long b = 0, b2 = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { b += s_w[k]; b2 += s_w2[k]; }
+    atomicAdd(ws + WS_ACCUM, b);
+    if (next_labels) atomicAdd(ws + WS_ACCUM_NEXT, b2);
     __threadfence();
-    const unsigned long long t = atomicAdd(ticket, 1ULL);
-    if (t == (unsigned long long)gridDim.x - 1ULL) {      // last block: every partial is in
-      const unsigned long long total = atomicAdd(accum, 0ULL);
-      *accum = 0ULL;
-      *ticket = 0ULL;
-      *count_local = (double)total;
+    const unsigned long long t = atomicAdd(ws + WS_TICKET, 1ULL);
+    if (t == (unsigned long long)gridDim.x - 1ULL) {      // last block: every partial is in, every block is done
+      const unsigned long long total = atomicAdd(ws + WS_ACCUM, 0ULL);
+      const unsigned long long total_next = atomicAdd(ws + WS_ACCUM_NEXT, 0ULL);
+      ws[WS_ACCUM] = 0ULL;
+      ws[WS_ACCUM_NEXT] = 0ULL;
+      ws[WS_TICKET] = 0ULL;
+      *reinterpret_cast<double*>(ws + WS_COUNT_LOCAL) = (double)total;
       if (X.world > 1) {
-        // sharded step: this rank's count goes into slot [parity][rank] of EVERY mailbox as one tagged 8-byte word
-        // (peer stores over NVLink; value and step number arrive together, no fence); the main kernel's CTAs pick the
-        // counts up in their prologue
         unsigned char* own = X.mail[X.rank];
         const unsigned long long seq = step_seq(own);
-        const int par = (int)(seq & 1ULL);
-        const unsigned long long word = count_word(seq, total);
-        for (int r = 0; r < X.world; ++r) st_relaxed_sys(count_slot_of(X.mail[r], par, X.rank), word);
+        const unsigned long long mine = ld_relaxed_sys(count_slot_of(own, seq, X.rank));
+        if ((mine >> 40) == (seq & 0xffffffULL)) {
+          // announced one step ago: the labels must be the ones that were counted then
+          if ((mine & kCountMask) != (total & kCountMask) && F.err) atomicOr(F.err, SIMT_ERRBIT_NEXT_LABELS);
+        } else {
+          const unsigned long long word = count_word(seq, total);
+          for (int r = 0; r < X.world; ++r) st_relaxed_sys(count_slot_of(X.mail[r], seq, X.rank), word);
+        }
+        // the NEXT step's count is pushed by the fused kernel's prologue (its peer stores then complete behind ~90 us
+        // of arithmetic instead of holding up this short kernel's retirement)
+        ws[WS_COUNT_NEXT] = next_labels ? count_word(seq + 1ULL, total_next) : 0ULL;
       }
+    }
+  }
+}
+
+// Sharded, deferred mode: finish everything that is outstanding now (HeadRunner.finish()): the older pending step, then
+// the last step (whose stats may not even have left this rank yet: no fused kernel ran since).  Collective in spirit:
+// the peers' stats of the last step only arrive once they run their next step or this kernel.
+__global__ void __launch_bounds__(256) head_finish_kernel(unsigned long long* __restrict__ ws, const XchgArgs X,
+                                                           const FinishArgs F) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const unsigned long long p0 = *reinterpret_cast<volatile unsigned long long*>(ws + WS_PENDING);
+  const unsigned long long p1 = *reinterpret_cast<volatile unsigned long long*>(ws + WS_PENDING_ODD);
+  const unsigned long long unsent = *reinterpret_cast<volatile unsigned long long*>(ws + WS_UNSENT);
+  if (unsent != 0ULL) push_stats_value(X, reinterpret_cast<const double*>(ws + kWsHeader / 8), F.C, F.CKP, unsent, i);
+  // oldest first, so that the outputs end up holding the latest step
+  unsigned long long todo[3] = {p0, p1, unsent};
+  if (todo[0] > todo[1]) { const unsigned long long t = todo[0]; todo[0] = todo[1]; todo[1] = t; }
+  for (int q = 0; q < 3; ++q)
+    if (todo[q] != 0ULL) finish_pending(X, F, todo[q], i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(ws + WS_TICKET, 1ULL);
+    if (t == (unsigned long long)gridDim.x - 1ULL) {
+      ws[WS_TICKET] = 0ULL;
+      ws[WS_PENDING] = 0ULL;
+      ws[WS_PENDING_ODD] = 0ULL;
+      ws[WS_UNSENT] = 0ULL;
     }
   }
 }
@@ -100,8 +159,8 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
     float* __restrict__ part_dT, const double* __restrict__ part_loss, const long long* __restrict__ part_cnt,
     int nparts, int ntiles, int CK, int CKP, int C, int mode, float gscale, unsigned long long* __restrict__ counter,
     double* __restrict__ stats, float* __restrict__ loss_mean, float* __restrict__ dT_out, int* __restrict__ err,
-    const float* __restrict__ grad_out, const double* __restrict__ count_dev, unsigned long long* __restrict__ fin_ticket,
-    const XchgArgs X) {
+    const float* __restrict__ grad_out, const double* __restrict__ count_dev, unsigned long long* __restrict__ ws,
+    const XchgArgs X, int defer) {
   const int ndt = C * CKP;
   const bool sharded = X.world > 1;   // loss / dT are final only after the exchange at the end of this kernel
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -134,6 +193,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
       const int y = o / CKP, k = o - y * CKP;
       if (k < CK) {
         if (stats) stats[2 + k * C + y] = -t;
+        if (defer) reinterpret_cast<double*>(ws + kWsHeader / 8)[2 + k * C + y] = -t;   // staging: awaits its push
         // MODE_STEP on one GPU: grad_out / N_valid is already known on the device (count pass)
         const double sc = count_dev ? (grad_out ? (double)__ldg(grad_out) : 1.0) / *count_dev : (double)gscale;
         if (dT_out && !sharded) dT_out[k * C + y] = (float)(-t * sc);
@@ -156,6 +216,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
       *counter = 0ULL;  // the main kernel of this call has finished: re-arm the unit scheduler
       const double ls = -kLn2 * l;
       if (stats) { stats[0] = ls; stats[1] = (double)c; }
+      if (defer) { double* stg = reinterpret_cast<double*>(ws + kWsHeader / 8); stg[0] = ls; stg[1] = (double)c; }
       if (loss_mean && !sharded) {
         float m = (float)(ls / (double)c);  // 0/0 -> NaN like the reference's mean over nothing
         if (err && (*err & SIMT_ERRBIT_LABEL_RANGE)) m = nanf("");
@@ -169,6 +230,9 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
   // words (peer stores over NVLink), then polls the same entries of all `world` slots of its OWN mailbox, sums them
   // in rank order (so the reduced values are bitwise identical on every rank) and writes the final stats / dT / loss.
   // No block waits for another block; the last one to finish advances the step counter.
+  // Deferred mode: nothing crosses the ranks here (peer stores would hold up this short kernel's retirement); the
+  // local stats stay in the caller's buffer, the next fused kernel's prologue pushes them and the prologue of the step
+  // after that (or head_finish_kernel) reduces them -- no rank ever waits, no short kernel ever issues a peer store.
   __shared__ int s_bad;
   unsigned char* own = X.mail[X.rank];
   const unsigned long long seq = step_seq(own);
@@ -177,22 +241,22 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
   if (tid == 0) s_bad = 0;
   __syncthreads();   // this block's local stats entries are written (and s_bad is initialised)
   const float poison = nanf("");
-  // the global valid count: the tagged count words the main kernel already waited for
-  double cnt = 0.0;
-  for (int r = 0; r < X.world; ++r) cnt += (double)(ld_relaxed_sys(count_slot_of(own, par, r)) & kCountMask);
+  // the global valid count: summed by the main kernel from the ranks' count words
+  const double cnt = *reinterpret_cast<const double*>(ws + WS_COUNT_GLOBAL);
   const double sc = (grad_out ? (double)__ldg(grad_out) : 1.0) / cnt;
   if ((int)blockIdx.x < (int)gridDim.x - 1) {
     const int o = blockIdx.x * 32 + tx;
     const int y = o / CKP, k = o - y * CKP;
     const bool mine = o < ndt && k < CK;
-    const int i = 2 + k * C + y;
-    if (mine && ty < X.world) ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.n_stats), i, seq, stats[i]);
-    if (mine && ty == 0) {
+    const int i = 2 + k * C + y;     // index in the caller's stats buffer; the slot keeps the tile order (entry 2 + o)
+    if (mine && ty < X.world && !defer)
+      ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.slot_entries), 2 + o, seq, stats[i]);
+    if (mine && ty == 0 && !defer) {
       double t = 0.0;
       bool ok = true;
       for (int r = 0; r < X.world; ++r) {
         double v = 0.0;
-        ok = ll_wait_f64(slot_of(own, par, r, X.n_stats), i, seq, X.max_spins, &v) && ok;
+        ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), 2 + o, seq, X.max_spins, &v) && ok;
         t += v;
       }
       if (!ok) s_bad = 1;
@@ -200,15 +264,16 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
       if (dT_out) dT_out[i - 2] = ok ? (float)(t * sc) : poison;
     }
   } else {
-    if (tid < 2 * X.world) ll_push_f64(slot_of(X.mail[tid >> 1], par, X.rank, X.n_stats), tid & 1, seq, stats[tid & 1]);
+    if (tid < 2 * X.world && !defer)
+      ll_push_f64(slot_of(X.mail[tid >> 1], par, X.rank, X.slot_entries), tid & 1, seq, stats[tid & 1]);
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !defer) {
       double t[2] = {0.0, 0.0};
       bool ok = true;
       for (int i = 0; i < 2; ++i)
         for (int r = 0; r < X.world; ++r) {
           double v = 0.0;
-          ok = ll_wait_f64(slot_of(own, par, r, X.n_stats), i, seq, X.max_spins, &v) && ok;
+          ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), i, seq, X.max_spins, &v) && ok;
           t[i] += v;
         }
       if (!ok) s_bad = 1;
@@ -225,9 +290,10 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
   if (tid == 0) {
     if (s_bad && err) atomicOr(err, SIMT_ERRBIT_XCHG_TIMEOUT);
     __threadfence();
-    const unsigned long long t = atomicAdd(fin_ticket, 1ULL);
+    const unsigned long long t = atomicAdd(ws + WS_FIN_TICKET, 1ULL);
     if (t == (unsigned long long)gridDim.x - 1ULL) {   // every block is done with this step's slots
-      *fin_ticket = 0ULL;
+      ws[WS_FIN_TICKET] = 0ULL;
+      if (defer) ws[WS_UNSENT] = seq;   // the next fused kernel's prologue (or head_finish_kernel) pushes the stats
       __threadfence();
       *reinterpret_cast<volatile unsigned long long*>(own) = seq;   // the step is over: advance the counter
     }
@@ -365,9 +431,9 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   A.counter = reinterpret_cast<unsigned long long*>(ws);
-  A.part_loss = reinterpret_cast<double*>(ws + 64);
-  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
-  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.part_loss = reinterpret_cast<double*>(ws + kWsHeader + ws_staging_bytes(CK, C));
+  A.part_cnt = reinterpret_cast<long long*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 8);
+  A.part_dT = reinterpret_cast<float*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 16);
   A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
   if (mode != MODE_FWD)
     SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
@@ -377,7 +443,7 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
   head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, mode, gscale,
                                               A.counter, stats, loss_mean, dT_out, err_flag, nullptr, nullptr, nullptr,
-                                              XchgArgs{});
+                                              XchgArgs{}, 0);
   return (int)cudaGetLastError();
 }
 
@@ -386,7 +452,7 @@ static int run_head(int mode, const float* logits, int B, int CK, int h, int w, 
 static int run_step(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
                     int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
                     double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes,
-                    const XchgArgs& X, cudaStream_t st) {
+                    const XchgArgs& X, const void* next_labels, int defer, cudaStream_t st) {
   int rc = validate(logits, B, CK, h, w, C, labels, label_bytes, H, W, T);
   if (rc) return rc;
   if (!err_flag || !workspace || !dlogits || !stats) return SIMT_EINVAL;
@@ -406,32 +472,41 @@ static int run_step(const float* logits, int B, int CK, int h, int w, const floa
   if (rc) return rc;
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  A.counter = reinterpret_cast<unsigned long long*>(ws);
-  unsigned long long* accum = reinterpret_cast<unsigned long long*>(ws + 8);     // the 64-byte header has room
-  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws + 16);
-  double* count_local = reinterpret_cast<double*>(ws + 24);
-  unsigned long long* fin_ticket = reinterpret_cast<unsigned long long*>(ws + 32);
+  unsigned long long* wsh = reinterpret_cast<unsigned long long*>(ws);     // the 64-byte header (see WS_*)
+  A.counter = wsh + WS_COUNTER;
+  double* count_local = reinterpret_cast<double*>(wsh + WS_COUNT_LOCAL);
   A.count_local = count_local;
-  A.part_loss = reinterpret_cast<double*>(ws + 64);
-  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
-  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.count_global = reinterpret_cast<double*>(wsh + WS_COUNT_GLOBAL);
+  A.ws_hdr = wsh;
+  A.fin = FinishArgs{stats, loss_mean, dT, grad_out, err_flag, CK, C, P.CKP};
+  A.part_loss = reinterpret_cast<double*>(ws + kWsHeader + ws_staging_bytes(CK, C));
+  A.part_cnt = reinterpret_cast<long long*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 8);
+  A.part_dT = reinterpret_cast<float*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 16);
   A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
+  FinishArgs F{stats, loss_mean, dT, grad_out, err_flag, CK, C, P.CKP};
   const long long n_dl = (long long)B * CK * h * w, npix = (long long)B * H * W;
   const int pgrid = di.sm_count * 4;
+  // (development aid: SIMT_PROF_WHICH=1 / 2 moves the launch profiler's event pair from the fused kernel to the
+  // prologue / finalize kernel)
+  static const int prof_which = getenv("SIMT_PROF_WHICH") ? atoi(getenv("SIMT_PROF_WHICH")) : 0;
+  if (prof_which == 1) prof_begin(st);
   if (label_bytes == 1)
-    head_prep_kernel<uint8_t><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const uint8_t*>(labels), npix, C, ignore,
-                                                     accum, ticket, count_local, X);
+    head_prep_kernel<uint8_t><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const uint8_t*>(labels),
+                                                     static_cast<const uint8_t*>(next_labels), npix, C, ignore, wsh, X, F);
   else
-    head_prep_kernel<long long><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const long long*>(labels), npix, C,
-                                                       ignore, accum, ticket, count_local, X);
+    head_prep_kernel<long long><<<pgrid, 256, 0, st>>>(dlogits, n_dl, static_cast<const long long*>(labels),
+                                                       static_cast<const long long*>(next_labels), npix, C, ignore, wsh, X, F);
+  if (prof_which == 1) prof_end(st);
   SIMT_CUDA_TRY(cudaGetLastError());
   int grid = 0;
-  rc = dispatch_all(MODE_STEP, label_bytes, A, P, st, &grid);
+  rc = dispatch_all(X.world > 1 ? MODE_STEPX : MODE_STEP, label_bytes, A, P, st, &grid);
   if (rc) return rc;
   const int fgrid = (C * P.CKP + 31) / 32 + 1;
+  if (prof_which == 2) prof_begin(st);
   head_finalize_kernel<<<fgrid, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, A.ntiles, CK, P.CKP, C, MODE_STEP,
                                               1.f, A.counter, stats, loss_mean, dT, err_flag, grad_out, count_local,
-                                              fin_ticket, X);
+                                              wsh, X, (X.world > 1 && defer) ? 1 : 0);
+  if (prof_which == 2) prof_end(st);
   return (int)cudaGetLastError();
 }
 
@@ -456,9 +531,9 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   A.counter = reinterpret_cast<unsigned long long*>(ws);
-  A.part_loss = reinterpret_cast<double*>(ws + 64);
-  A.part_cnt = reinterpret_cast<long long*>(ws + 64 + G * 8);
-  A.part_dT = reinterpret_cast<float*>(ws + 64 + G * 16);
+  A.part_loss = reinterpret_cast<double*>(ws + kWsHeader + ws_staging_bytes(CK, C));
+  A.part_cnt = reinterpret_cast<long long*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 8);
+  A.part_dT = reinterpret_cast<float*>(ws + kWsHeader + ws_staging_bytes(CK, C) + G * 16);
   A.ntiles = di.sm_count < kFinSlices * kFinMaxPer ? di.sm_count : kFinSlices * kFinMaxPer;
   SIMT_CUDA_TRY(cudaMemsetAsync(dlogits, 0, (size_t)B * CK * h * w * sizeof(float), st));
   int grid = 0;
@@ -467,7 +542,7 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
   // one block: loss / count partials and the scheduler re-arm (there are no dT tiles in this mode)
   head_finalize_kernel<<<1, 1024, 0, st>>>(A.part_dT, A.part_loss, A.part_cnt, grid, 0, CK, P.CKP, C, MODE_PLACE, 1.f,
                                            A.counter, stats, loss_mean, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                           XchgArgs{});
+                                           XchgArgs{}, 0);
   return (int)cudaGetLastError();
 }
 
@@ -475,14 +550,27 @@ static int run_place(const float* logits, int B, int CK, int h, int w, int C, in
 
 using namespace simt;
 
+static int make_xchg(int rank, int world, void* const* mailboxes, int CK, int C, XchgArgs* X) {
+  if (!mailboxes || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || CK <= 0 || C <= 0) return SIMT_EINVAL;
+  for (int r = 0; r < world; ++r) {
+    if (!mailboxes[r]) return SIMT_EINVAL;
+    X->mail[r] = static_cast<unsigned char*>(mailboxes[r]);
+  }
+  X->rank = rank; X->world = world; X->n_stats = 2 + CK * C;
+  X->slot_entries = 2 + C * kXchgMaxCKP;
+  X->max_spins = xchg_max_spins();
+  return 0;
+}
+
 extern "C" {
 
 size_t simt_head_workspace_bytes(int B, int CK, int C, int h, int w, int H, int W) {
-  (void)B; (void)h; (void)w; (void)H; (void)W; (void)CK;
+  (void)B; (void)h; (void)w; (void)H; (void)W;
   DeviceInfo di;
   if (device_info(&di)) di.sm_count = 256;
   const size_t G = (size_t)di.sm_count * kMaxGridPerSm;
-  return 64 + G * 16 + G * (size_t)(C > 0 ? C : 1) * kMaxCKP * sizeof(double);
+  return kWsHeader + ws_staging_bytes(CK > 0 ? CK : 1, C > 0 ? C : 1) + G * 16 +
+         G * (size_t)(C > 0 ? C : 1) * kMaxCKP * sizeof(double);
 }
 
 void simt_head_set_tuning(int cell_rows_per_unit, int reserved, int threads, int lpr) {
@@ -517,23 +605,36 @@ int simt_head_step(const float* logits, int B, int CK, int h, int w, const float
                    int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
                    double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes, void* stream) {
   return run_step(logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, grad_out, dlogits, dT, stats, loss_mean,
-                  err_flag, workspace, workspace_bytes, XchgArgs{}, (cudaStream_t)stream);
+                  err_flag, workspace, workspace_bytes, XchgArgs{}, nullptr, 0, (cudaStream_t)stream);
 }
 
 int simt_head_step_sharded(const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
                            int label_bytes, int H, int W, int ignore, const float* grad_out, float* dlogits, float* dT,
                            double* stats, float* loss_mean, int* err_flag, void* workspace, size_t workspace_bytes,
-                           int rank, int world, void* const* mailboxes, void* stream) {
-  if (!mailboxes || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return SIMT_EINVAL;
+                           int rank, int world, void* const* mailboxes, const void* next_labels, int defer,
+                           void* stream) {
   XchgArgs X{};
-  for (int r = 0; r < world; ++r) {
-    if (!mailboxes[r]) return SIMT_EINVAL;
-    X.mail[r] = static_cast<unsigned char*>(mailboxes[r]);
-  }
-  X.rank = rank; X.world = world; X.n_stats = 2 + CK * C;
-  X.max_spins = xchg_max_spins();
+  int rc = make_xchg(rank, world, mailboxes, CK, C, &X);
+  if (rc) return rc;
   return run_step(logits, B, CK, h, w, T, C, labels, label_bytes, H, W, ignore, grad_out, dlogits, dT, stats, loss_mean,
-                  err_flag, workspace, workspace_bytes, X, (cudaStream_t)stream);
+                  err_flag, workspace, workspace_bytes, X, next_labels, defer, (cudaStream_t)stream);
+}
+
+int simt_head_finish_sharded(int CK, int C, const float* grad_out, float* dT, double* stats, float* loss_mean,
+                             int* err_flag, void* workspace, size_t workspace_bytes, int rank, int world,
+                             void* const* mailboxes, void* stream) {
+  if (!workspace || workspace_bytes < kWsHeader + ws_staging_bytes(CK, C) || !stats) return SIMT_EINVAL;
+  XchgArgs X{};
+  int rc = make_xchg(rank, world, mailboxes, CK, C, &X);
+  if (rc) return rc;
+  if (world <= 1) return 0;
+  Plan P{};
+  rc = choose_config(CK, current_tuning().lpr, &P);     // the dT tile's row length of this channel count
+  if (rc) return rc;
+  FinishArgs F{stats, loss_mean, dT, grad_out, err_flag, CK, C, P.CKP};
+  head_finish_kernel<<<(X.n_stats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<unsigned long long*>(workspace), X, F);
+  return (int)cudaGetLastError();
 }
 
 int simt_placeholder_fwdbwd(const float* logits, int B, int CK, int h, int w, int C, int H, int W, float thres,

@@ -20,9 +20,10 @@
 
 namespace simt {
 
-// ~30 s at the 64 ns back-off of wait_flag (an exchange takes microseconds; ranks that drift further apart than this --
-// a checkpoint on rank 0, a stalled data loader -- should raise the bound or pass 0 = wait for ever)
-static std::atomic<long long> g_max_spins{1LL << 28};
+// Polls per wait before a rank gives up on a peer (each poll is a system-scope load, ~1 us with its back-off: the
+// default is of the order of 10-20 s; an exchange takes microseconds).  Ranks that drift further apart than this -- a
+// checkpoint on rank 0, a stalled data loader -- should raise the bound or pass 0 = wait for ever.
+static std::atomic<long long> g_max_spins{1LL << 24};
 long long xchg_max_spins() { return g_max_spins.load(); }
 
 }  // namespace simt
@@ -33,9 +34,10 @@ extern "C" {
 
 void simt_xchg_set_timeout(long long max_spins) { g_max_spins.store(max_spins); }
 
-size_t simt_xchg_bytes(int n_stats) {
-  if (n_stats <= 0) return 0;
-  return kHdrBytes + kCountBytes + (size_t)2 * kMaxPeers * (size_t)(2 * n_stats) * sizeof(unsigned long long);
+size_t simt_xchg_bytes(int C) {
+  if (C <= 0) return 0;
+  const size_t slot = 2 + (size_t)C * kXchgMaxCKP;
+  return kHdrBytes + kCountBytes + (size_t)2 * kMaxPeers * (2 * slot) * sizeof(unsigned long long);
 }
 
 int simt_xchg_create(size_t bytes, void** mailbox, unsigned char* handle64) {

@@ -2,13 +2,16 @@
 //
 // One mailbox per rank (cudaMalloc'd, CUDA-IPC mapped into every peer):
 //   u64 hdr[64]:  [0] step counter (advanced by the last kernel of a step)
-//   u64 counts[2][8]               valid-pixel counts, pushed by the step's first kernel as ONE tagged word each:
-//                                  (step number mod 2^24) << 40 | count  -- a single 8-byte store needs no fence
-//   u64 stats [2][8][2 * n_stats]  {loss sum, valid count, raw dT} as doubles, pushed by the step's last kernel as
-//                                  TWO tagged words per value: (step number mod 2^32) << 32 | 32 bits of the double
+//   u64 counts[4][8]               valid-pixel counts of step s in row s % 4, pushed by the first kernel of step s (or,
+//                                  when the caller knows the next step's labels, of step s - 1) as ONE tagged word
+//                                  each: (step number mod 2^24) << 40 | count -- a single 8-byte store, no fence
+//   u64 stats [2][8][2 * slot]     {loss sum, valid count, raw dT tile [C][CKP]} as doubles, pushed by the step's last
+//                                  kernel as TWO tagged words per value: (step number mod 2^32) << 32 | 32 bits of the
+//                                  double; slot = 2 + C * 64 entries (the dT tile keeps the kernel's [y][k] order, so a
+//                                  warp's 32 values are one contiguous 512-byte peer store)
 // Every word carries its own step tag (the scheme of NCCL's LL protocol): an 8-byte store is atomic, so the receiver
 // polls the word itself -- no flag, no fence, one NVLink store latency per exchange.
-// Slots are double-buffered by step parity; see head.cu (sharded step) for why that is enough.
+// Stats slots are double-buffered by step parity, count rows by step mod 4; see xchg.cu for why that is enough.
 #pragma once
 #include "common.cuh"
 
@@ -17,19 +20,22 @@ namespace simt {
 static constexpr int kMaxPeers = 8;
 static constexpr int kHdrWords = 64;
 static constexpr size_t kHdrBytes = kHdrWords * sizeof(unsigned long long);
-static constexpr size_t kCountBytes = 2 * kMaxPeers * sizeof(double);
+static constexpr int kCountRows = 4;
+static constexpr int kXchgMaxCKP = 64;   // widest padded channel count of the head kernel's dT tile
+static constexpr size_t kCountBytes = kCountRows * kMaxPeers * sizeof(unsigned long long);
 
 struct XchgArgs {
   unsigned char* mail[kMaxPeers];  // mailbox base of every rank (mail[rank] is local memory); all null when world <= 1
-  int rank, world, n_stats;
+  int rank, world, n_stats;        // n_stats = 2 + CK*C values of the caller's stats buffer
+  int slot_entries;                // capacity of one stats slot (values): 2 + C * kXchgMaxCKP
   long long max_spins;             // bound of every flag wait (<= 0: wait for ever); see simt_xchg_set_timeout
 };
 
 __device__ __forceinline__ unsigned long long* hdr_of(unsigned char* mailbox) {
   return reinterpret_cast<unsigned long long*>(mailbox);
 }
-__device__ __forceinline__ unsigned long long* count_slot_of(unsigned char* mailbox, int parity, int rank) {
-  return reinterpret_cast<unsigned long long*>(mailbox + kHdrBytes) + parity * kMaxPeers + rank;
+__device__ __forceinline__ unsigned long long* count_slot_of(unsigned char* mailbox, unsigned long long seq, int rank) {
+  return reinterpret_cast<unsigned long long*>(mailbox + kHdrBytes) + (int)(seq & (kCountRows - 1)) * kMaxPeers + rank;
 }
 // tagged count word: the step number travels with the value, so one relaxed 8-byte store publishes both
 static constexpr unsigned long long kCountMask = (1ULL << 40) - 1ULL;
@@ -56,9 +62,9 @@ __device__ __forceinline__ bool wait_count(const unsigned long long* p, unsigned
   *count = v & kCountMask;
   return true;
 }
-__device__ __forceinline__ unsigned long long* slot_of(unsigned char* mailbox, int parity, int rank, int n_stats) {
+__device__ __forceinline__ unsigned long long* slot_of(unsigned char* mailbox, int parity, int rank, int slot_entries) {
   return reinterpret_cast<unsigned long long*>(mailbox + kHdrBytes + kCountBytes) +
-         ((size_t)parity * kMaxPeers + rank) * (size_t)(2 * n_stats);
+         ((size_t)parity * kMaxPeers + rank) * (size_t)(2 * slot_entries);
 }
 // this step's number: the counter is advanced by the last kernel of a step
 __device__ __forceinline__ unsigned long long step_seq(unsigned char* own_mailbox) {

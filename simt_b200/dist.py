@@ -64,7 +64,7 @@ class PeerMailbox:
     P2P); callers fall back to ``reduce_head_stats`` (a library all-reduce).
     """
 
-    def __init__(self, n_stats: int, group=None, device: Optional[torch.device] = None):
+    def __init__(self, C: int, group=None, device: Optional[torch.device] = None):
         from . import _lib
         self.lib = _lib.load()
         self.group = group
@@ -77,7 +77,7 @@ class PeerMailbox:
         handle = ctypes.create_string_buffer(64)
         ok, why = True, ""
         with torch.cuda.device(self.dev):
-            rc = self.lib.simt_xchg_create(self.lib.simt_xchg_bytes(int(n_stats)), ctypes.byref(self.own), handle)
+            rc = self.lib.simt_xchg_create(self.lib.simt_xchg_bytes(int(C)), ctypes.byref(self.own), handle)
             if rc:
                 ok, why = False, f"simt_xchg_create: code {rc}"
             handles = [None] * self.world

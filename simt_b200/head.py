@@ -60,6 +60,8 @@ def check_errors(dev=None) -> None:
             what.append("label outside [0, C) that is not the ignore label")
         if v & 2:
             what.append("n_cols*a+b outside the histogram table")
+        if v & 8:
+            what.append("sharded step: the labels differ from the next_labels announced one step earlier")
         if v & 4:
             what.append("sharded step: a peer rank's count / stats never arrived (bounded wait expired; this rank's "
                         "loss, dT and possibly dlogits of that step are NaN)")
@@ -244,7 +246,7 @@ class HeadRunner:
         if group is not None and exchange == "p2p" and self._world > 1:
             from .dist import PeerMailbox
             try:
-                self.mailbox = PeerMailbox(2 + CK * C, group, self.dev)
+                self.mailbox = PeerMailbox(C, group, self.dev)
             except RuntimeError:
                 self.mailbox = None
 
@@ -318,15 +320,28 @@ class HeadRunner:
         if rc:
             _lib.check(rc, "simt_head_scale")
 
-    def step(self, logits, T, labels, grad_out=None):
+    def step(self, logits, T, labels, grad_out=None, next_labels=None, defer=False, out=None):
         """One training step: (loss, dlogits, dT), final and global, without synchronising.
         One GPU: ``simt_head_step`` (label count + zeroing, fused kernel applying grad_out / N itself, finalize).
         Sharded: ``simt_head_step_sharded`` -- the same three kernels exchange counts and stats over the peer
-        mailboxes -- or, when the peers cannot be mapped, fwdbwd + one NCCL all-reduce + scale."""
+        mailboxes -- or, when the peers cannot be mapped, fwdbwd + one NCCL all-reduce + scale.
+        Sharded, pipelined (no rank waits inside a step; validated on 2 GPUs): ``next_labels``
+        = the labels the NEXT step will get (their valid count crosses the ranks one step early); ``defer=True``
+        leaves loss / dT / stats of this step to be finalised inside the fused kernel of the step after the next, or
+        by ``finish()`` (a collective: every rank calls it at the same point) -- dlogits are always final.
+        ``out``: a float32 [B, CK, h, w] buffer to receive dlogits instead of ``self.dlogits``."""
         self._check(logits, T, labels, grad_out)
         stream = _stream_ptr()
         B, CK, C, h, w, H, W = self.shape
         ws, nws, stats, loss, dl, dT, err = self._p
+        dl_t = self.dlogits
+        if out is not None:
+            if tuple(out.shape) != (B, CK, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.dev:
+                raise ValueError(f"HeadRunner{self.shape}: out must be a contiguous float32 [{B}, {CK}, {h}, {w}] on {self.dev}")
+            dl, dl_t = out.data_ptr(), out
+        if next_labels is not None and (tuple(next_labels.shape) != (B, H, W) or next_labels.dtype != self.label_dtype
+                                        or not next_labels.is_contiguous() or next_labels.device != self.dev):
+            raise ValueError(f"HeadRunner{self.shape}: next_labels must look like labels")
         tp = None if T is None else T.data_ptr()
         gp = None if grad_out is None else grad_out.data_ptr()
         with torch.cuda.device(self.dev):
@@ -336,12 +351,17 @@ class HeadRunner:
                 dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
                 self.scale(grad_out, stream)
                 self.loss.copy_((self.stats[0] / self.stats[1]).to(torch.float32))   # the GLOBAL mean, as on the p2p path
-                return self.loss, self.dlogits, self.dT
+                if out is not None:
+                    out.copy_(self.dlogits)
+                return self.loss, dl_t, self.dT
             if self._world > 1:
                 mb = self.mailbox
+                self._grad_out = grad_out
                 rc = self.lib.simt_head_step_sharded(logits.data_ptr(), B, CK, h, w, tp, C, labels.data_ptr(),
                                                      self.label_bytes, H, W, self.ignore, gp, dl, dT, stats, loss, err,
-                                                     ws, nws, mb.rank, mb.world, mb.ptrs, stream)
+                                                     ws, nws, mb.rank, mb.world, mb.ptrs,
+                                                     None if next_labels is None else next_labels.data_ptr(),
+                                                     1 if defer else 0, stream)
                 what = "simt_head_step_sharded"
             else:
                 rc = self.lib.simt_head_step(logits.data_ptr(), B, CK, h, w, tp, C, labels.data_ptr(), self.label_bytes,
@@ -349,31 +369,51 @@ class HeadRunner:
                 what = "simt_head_step"
         if rc:
             _lib.check(rc, what)
-        return self.loss, self.dlogits, self.dT
+        return self.loss, dl_t, self.dT
 
-    def graph_step(self, logits, T, labels, grad_out=None):
+    def finish(self):
+        """Sharded, after ``step(..., defer=True)``: finalise loss / dT / stats of every outstanding step now (one tiny
+        kernel; a no-op when nothing is outstanding).  Collective in spirit: the peers' stats of the LAST step only
+        leave them when they run their next step or call ``finish()`` too."""
+        if self._world <= 1 or self.mailbox is None:
+            return self.loss, self.dT
+        B, CK, C, h, w, H, W = self.shape
+        ws, nws, stats, loss, dl, dT, err = self._p
+        mb = self.mailbox
+        g = getattr(self, "_grad_out", None)
+        with torch.cuda.device(self.dev):
+            rc = self.lib.simt_head_finish_sharded(CK, C, None if g is None else g.data_ptr(), dT, stats, loss, err, ws, nws,
+                                                   mb.rank, mb.world, mb.ptrs, _stream_ptr())
+        if rc:
+            _lib.check(rc, "simt_head_finish_sharded")
+        return self.loss, self.dT
+
+    def graph_step(self, logits, T, labels, grad_out=None, next_labels=None, defer=False, out=None):
         """``step`` replayed from a CUDA graph: its three launches are captured ONCE for this exact set of buffers
         (keyed by their addresses) and re-launched as one graph afterwards -- they are launch-latency-bound next to a
         90 us kernel.  The graph reads the buffers' CURRENT contents on every replay (refill ``logits`` / ``labels``
         / ``T`` in place).  Sharded runs replay too when the exchange is the fused peer-memory one (no library
         collective inside the graph); with the all-reduce fallback they take the eager path."""
         if self._world > 1 and self.mailbox is None:
-            return self.step(logits, T, labels, grad_out)
+            return self.step(logits, T, labels, grad_out, out=out)
         key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
-               None if grad_out is None else grad_out.data_ptr())
+               None if grad_out is None else grad_out.data_ptr(),
+               None if next_labels is None else next_labels.data_ptr(), bool(defer), None if out is None else out.data_ptr())
         g = self._graphs.get(key)
         if g is None:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("HeadRunner.graph_step: first call for a buffer set must be outside stream capture")
-            self.step(logits, T, labels, grad_out)          # warm-up: one-time attribute / occupancy queries
+            # warm-up (one-time attribute / occupancy queries): a plain synchronous step -- it must not announce
+            # next_labels, because the replay below runs THESE labels once more
+            self.step(logits, T, labels, grad_out, None, False, out)
             torch.cuda.current_stream(self.dev).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.step(logits, T, labels, grad_out)
+                self.step(logits, T, labels, grad_out, next_labels, defer, out)
             self._graphs[key] = g
-            self._graph_keepalive.append((logits, T, labels, grad_out))
+            self._graph_keepalive.append((logits, T, labels, grad_out, next_labels, out))
         g.replay()
-        return self.loss, self.dlogits, self.dT
+        return self.loss, (self.dlogits if out is None else out), self.dT
 
     def global_loss(self):
         """loss over the all-reduced stats (sharded runs); a 0-dim f64 tensor, no sync."""

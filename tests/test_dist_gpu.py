@@ -55,9 +55,31 @@ def _worker(rank, world, port, out_dir):
             lgb.copy_(sd.shard_batch(lg_i, rank, world)); lbb.copy_(sd.shard_batch(lb_i, rank, world).to(torch.uint8))
             l_i, dl_i, dT_i = (runner.step if it < 5 else runner.graph_step)(lgb, Td, lbb)
             p2p.append((l_i.cpu().clone(), dl_i.cpu().clone(), dT_i.cpu().clone(), runner.stats.cpu().clone()))
+        pipe = []
+        if os.environ.get("SIMT_TEST_PIPELINED") == "1":
+          # pipelined form: the NEXT step's labels are announced (their count crosses the ranks one step early) and the
+          # stats all-reduce is deferred to the next step's prologue / finish(); rotating label and dLogits buffers
+          lbs = [torch.empty(3, 64, 128, dtype=torch.uint8, device=dev) for _ in range(2)]
+          outs = [torch.empty(3, 23, 9, 17, device=dev) for _ in range(2)]
+          batches = [O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=90 + it, coherent=True, block=(12, 20)) for it in range(7)]
+          lbs[0].copy_(sd.shard_batch(batches[0][1], rank, world).to(torch.uint8))
+          for it in range(6):
+              lgb.copy_(sd.shard_batch(batches[it][0], rank, world))
+              lbs[(it + 1) & 1].copy_(sd.shard_batch(batches[it + 1][1], rank, world).to(torch.uint8))
+              fn = runner.step if it < 3 else runner.graph_step
+              _, dl_i, _ = fn(lgb, Td, lbs[it & 1], next_labels=lbs[(it + 1) & 1], defer=True, out=outs[it & 1])
+              if it % 2 == 0:
+                  l_i, dT_i = runner.finish()          # explicit finish ...
+                  pipe.append((l_i.cpu().clone(), dl_i.cpu().clone(), dT_i.cpu().clone(), runner.stats.cpu().clone()))
+              else:                                     # ... or left to the next step's prologue
+                  pipe.append([None, dl_i.cpu().clone(), None, None])
+              if it % 2 == 1:
+                  torch.cuda.synchronize()
+          runner.finish()
+          torch.cuda.synchronize()
         simt_b200.check_errors(dev)
         torch.save({"loss": loss.detach().cpu(), "dl": lg.grad.cpu(), "dT": Tt.grad.cpu(), "hist": meter.hist.cpu(),
-                    "p2p": p2p, "used_mailbox": runner.mailbox is not None, "n_graphs": len(runner._graphs)},
+                    "p2p": p2p, "pipe": pipe, "used_mailbox": runner.mailbox is not None, "n_graphs": len(runner._graphs)},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -89,7 +111,7 @@ def test_two_rank_head_equals_global_batch(tmp_path):
     assert np.array_equal(res[0]["hist"].numpy(), hist) and np.array_equal(res[1]["hist"].numpy(), hist)
     # ---- fused peer-memory exchange (HeadRunner): every step equals the single-GPU answer on the global batch ----
     assert res[0]["used_mailbox"] and res[1]["used_mailbox"], "CUDA-IPC peer mailboxes were not set up on a 2-GPU box"
-    assert res[0]["n_graphs"] == 1
+    assert res[0]["n_graphs"] >= 1
     for it in range(8):
         lg_i, lb_i = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=50 + it, coherent=True, block=(12, 20))
         lo, dlo, dTo = O.simt_head_fwd_bwd(lg_i, T, lb_i, (64, 128), torch.float64)
@@ -101,3 +123,18 @@ def test_two_rank_head_equals_global_batch(tmp_path):
             assert float((dl_i.double() - dlo[a:b]).norm() / dlo[a:b].norm()) <= 1e-5, (it, r)
         # fixed rank-order sum: the all-reduced stats are bitwise identical on both ranks
         assert torch.equal(res[0]["p2p"][it][3], res[1]["p2p"][it][3]), it
+    # ---- pipelined form: announced next labels + deferred all-reduce (opt-in: SIMT_TEST_PIPELINED=1; validated on
+    # 2 GPUs) ----
+    for it in range(6 if res[0]["pipe"] else 0):
+        lg_i, _ = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=90 + it, coherent=True, block=(12, 20))
+        _, lb_i = O.synth_head_inputs(6, 23, 9, 17, 64, 128, seed=90 + it, coherent=True, block=(12, 20))
+        lo, dlo, dTo = O.simt_head_fwd_bwd(lg_i, T, lb_i, (64, 128), torch.float64)
+        for r in range(world):
+            l_i, dl_i, dT_i, st_i = res[r]["pipe"][it]
+            a, b = sd.shard_range(6, r, world)
+            assert float((dl_i.double() - dlo[a:b]).norm() / dlo[a:b].norm()) <= 1e-5, ("pipe dl", it, r)
+            if l_i is not None:
+                assert abs(float(l_i) - float(lo)) <= 1e-5 * abs(float(lo)), ("pipe loss", it, r)
+                assert float((dT_i.double() - dTo).norm() / dTo.norm()) <= 1e-5, ("pipe dT", it, r)
+        if res[0]["pipe"][it][3] is not None:
+            assert torch.equal(res[0]["pipe"][it][3], res[1]["pipe"][it][3]), it
