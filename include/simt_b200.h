@@ -113,8 +113,9 @@ int simt_head_bwd(const float* logits, int B, int CK, int h, int w,
 int simt_head_scale(float* dlogits, long long n_dlogits, const double* stats, int CK, int C,
                     const float* grad_out, float* dT, void* stream);
 
-/* tuning hook for benchmarks (process-global, not thread-safe): tile size in
- * low-res cells, threads per CTA, lanes per pixel-run (1, 2 or 4); 0 = automatic. */
+/* tuning hook for benchmarks (process-global, mutex-guarded like the library's launch caches: the entry points may be
+ * called from several host threads, one stream / device each): cell-rows per work unit, row slices per cell-row,
+ * reserved, lanes per pixel-run (2 or 4); 0 = automatic. */
 void simt_head_set_tuning(int tile_cells_y, int tile_cells_x, int threads, int lanes_per_run);
 
 /* ------------------------------------------------------------------------- *
@@ -312,7 +313,9 @@ int simt_pseudo_labels(const float* fixed_logits_lo, const float* pred2_lo, int 
 int simt_eval_argmax(const float* logits_a, int CKa, int ha, int wa, const float* logits_b, int CKb, int hb, int wb,
                      int B, int C, int H, int W, uint8_t* pred_out, void* stream);
 
-/* benchmark hook (process-global): `mode` is reserved; warps per CTA and 128-bit loads in flight per lane; 0 = automatic */
+/* benchmark hook (process-global, mutex-guarded): warps per CTA and 128-bit loads in flight per lane; 0 = automatic.
+ * mode 0 = normal.  mode 9 = LOAD-ONLY PROBE for bandwidth measurements: the kernels stream their inputs with the
+ * production access pattern but skip the counting, so the histogram they return is meaningless -- never leave it on. */
 void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
 
 #ifdef __cplusplus

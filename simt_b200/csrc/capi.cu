@@ -1,4 +1,5 @@
 // ABI version, error strings and the launch profiler shared by all kernels.
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -12,8 +13,12 @@ struct Profiler {
   size_t used = 0;
 };
 static Profiler g_prof;
+static std::mutex g_prof_mutex;   // the profiler is process-global; launches may come from several host threads
 
-bool prof_enabled() { return g_prof.on; }
+bool prof_enabled() {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  return g_prof.on;
+}
 
 // events recorded into a capturing stream become graph nodes whose timestamps cannot be read back: skip them
 static bool capturing(cudaStream_t st) {
@@ -22,6 +27,7 @@ static bool capturing(cudaStream_t st) {
 }
 
 void prof_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   if (!g_prof.on || capturing(st)) return;
   if (g_prof.used == g_prof.starts.size()) {
     cudaEvent_t a, b;
@@ -33,6 +39,7 @@ void prof_begin(cudaStream_t st) {
 }
 
 void prof_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   if (!g_prof.on || g_prof.used >= g_prof.stops.size() || capturing(st)) return;
   cudaEventRecord(g_prof.stops[g_prof.used], st);
   ++g_prof.used;
@@ -60,11 +67,13 @@ const char* simt_b200_strerror(int code) {
 }
 
 void simt_b200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof.on = on != 0;
   g_prof.used = 0;
 }
 
 int simt_b200_profile_read(double* total_ms, long long* launches) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   double tot = 0;
   for (size_t i = 0; i < g_prof.used; ++i) {
     SIMT_CUDA_TRY(cudaEventSynchronize(g_prof.stops[i]));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <mutex>
 #include "../../include/simt_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -22,13 +23,20 @@ struct DeviceInfo {
   int smem_optin;  // max dynamic shared memory per CTA (bytes)
 };
 
-// Per-device cache (the only global state besides the tuning hooks).
+// One mutex for the library's small per-device caches (attribute queries, function attributes).
+inline std::mutex& cache_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+// Per-device cache (the only global state besides the tuning hooks and the launch profiler; all mutex-guarded).
 inline int device_info(DeviceInfo* out) {
   static DeviceInfo cache[64];
   static bool have[64] = {};
   int dev = 0;
   SIMT_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return SIMT_EUNSUPPORTED;
+  std::lock_guard<std::mutex> lock(cache_mutex());
   if (!have[dev]) {
     DeviceInfo d;
     SIMT_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -47,6 +55,7 @@ inline int ensure_dynamic_smem(Kernel kernel, bool (&done)[64], int bytes) {
   int dev = 0;
   SIMT_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return SIMT_EUNSUPPORTED;
+  std::lock_guard<std::mutex> lock(cache_mutex());
   if (!done[dev]) {
     SIMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done[dev] = true;

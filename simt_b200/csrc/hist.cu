@@ -18,12 +18,20 @@
 //   a 32-way same-address conflict.  At the end the CTA adds its copies to the caller's int64
 //   table with one global atomic per non-zero bin.
 // int64 inputs (the dtype label_mapping returns) take a generic, slower kernel.
+#include <mutex>
 #include "common.cuh"
 
 namespace simt {
 
+// Benchmark tuning hook (simt_hist_set_tuning) and the lazily allocated scratch word of simt_class_hist: process-global,
+// guarded by one mutex so that the entry points may be called from several host threads.
 struct HistTuning { int mode, warps, unroll; };
 static HistTuning g_hist_tuning = {0, 0, 0};
+static std::mutex g_hist_mutex;
+static HistTuning current_hist_tuning() {
+  std::lock_guard<std::mutex> lock(g_hist_mutex);
+  return g_hist_tuning;
+}
 
 // ------------------------------------------------------------------------------------------
 // uint8 fast path
@@ -248,6 +256,7 @@ static int run_hist(const void* a, int a_bytes, const void* b, int b_bytes, long
   int rc = device_info(&di);
   if (rc) return rc;
   const long long nbins = (long long)n_rows * n_cols;
+  const HistTuning tune = current_hist_tuning();
   unsigned long long* h = reinterpret_cast<unsigned long long*>(hist);
   const bool fast = a_bytes == 1 && (!b || b_bytes == 1) && nbins <= 1024 && n_rows <= 256 &&
                     (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0);
@@ -258,10 +267,10 @@ static int run_hist(const void* a, int a_bytes, const void* b, int b_bytes, long
       A.a = static_cast<const uint8_t*>(a) + off;
       A.b = b ? static_cast<const uint8_t*>(b) + off : nullptr;
       A.n = len; A.lut = lut; A.n_rows = n_rows; A.n_cols = n_cols; A.nbins = (int)nbins;
-      A.hist = h; A.err = err_flag; A.probe = (g_hist_tuning.mode == 9);
+      A.hist = h; A.err = err_flag; A.probe = (tune.mode == 9);
       // more loads in flight per lane pay off once the launch is long enough to reach steady state
-      int unroll = g_hist_tuning.unroll > 0 ? g_hist_tuning.unroll : (len >= (1LL << 29) ? 4 : 1);
-      int warps = g_hist_tuning.warps > 0 ? g_hist_tuning.warps : 16;
+      int unroll = tune.unroll > 0 ? tune.unroll : (len >= (1LL << 29) ? 4 : 1);
+      int warps = tune.warps > 0 ? tune.warps : 16;
       if (warps > 16) warps = 16;
       const size_t smem = 256 + (size_t)kRep * ((size_t)A.nbins | 1) * 4;   // <= 33 KB for 1024 bins
       int ctas_per_sm = 2048 / (warps * 32);
@@ -299,7 +308,10 @@ using namespace simt;
 
 extern "C" {
 
-void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll) { g_hist_tuning = {mode, warps_per_cta, unroll}; }
+void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll) {
+  std::lock_guard<std::mutex> lock(g_hist_mutex);
+  g_hist_tuning = {mode, warps_per_cta, unroll};
+}
 
 int simt_confusion(const void* a, int a_bytes, const void* b, int b_bytes, long long n, const uint8_t* lut256,
                    int n_rows, int n_cols, long long* hist, int* err_flag, void* stream) {
@@ -314,9 +326,12 @@ int simt_class_hist(const void* a, int a_bytes, long long n, int n_bins, long lo
   int dev = 0;
   SIMT_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return SIMT_EUNSUPPORTED;
-  if (!dummy_err[dev]) {
-    SIMT_CUDA_TRY(cudaMalloc(&dummy_err[dev], sizeof(int)));
-    SIMT_CUDA_TRY(cudaMemset(dummy_err[dev], 0, sizeof(int)));
+  {
+    std::lock_guard<std::mutex> lock(g_hist_mutex);
+    if (!dummy_err[dev]) {
+      SIMT_CUDA_TRY(cudaMalloc(&dummy_err[dev], sizeof(int)));
+      SIMT_CUDA_TRY(cudaMemset(dummy_err[dev], 0, sizeof(int)));
+    }
   }
   return run_hist(a, a_bytes, nullptr, 0, n, nullptr, n_bins, 1, hist, dummy_err[dev], (cudaStream_t)stream);
 }

@@ -106,15 +106,30 @@ def per_class_iu(hist):
         return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
 
 
+def _label_mapping_generic(x: torch.Tensor, mapping) -> torch.Tensor:
+    """tools/compute_iou.py:18-22 for any integer dtype: ``out = copy(input); out[input == k] = v`` for every (k, v) in
+    order (matches are on the ORIGINAL input; values that are no key stay as they are), int64 result.  Stock torch ops
+    on the tensor's own device -- the LUT kernel below covers the uint8 images PIL yields."""
+    out = x.to(torch.int64).clone()
+    for k, v in mapping:
+        out[x == int(k)] = int(v)
+    return out
+
+
 def label_mapping(input, mapping):
-    """uint8 raw-id image -> int64 train-id image through the LUT kernel."""
+    """raw-id image -> int64 train-id image (tools/compute_iou.py:18-22): uint8 images through the 256-entry LUT
+    kernel, any other integer dtype through a torch-op composition on the device."""
     lib = _lib.load()
     as_numpy = isinstance(input, np.ndarray)
-    if as_numpy and input.dtype != np.uint8:
-        raise TypeError("simt_b200.label_mapping takes uint8 images (what PIL yields for Cityscapes label PNGs)")
-    if isinstance(input, torch.Tensor) and input.dtype != torch.uint8:
-        raise TypeError("simt_b200.label_mapping takes uint8 images")
     dev = input.device if isinstance(input, torch.Tensor) and input.is_cuda else _dev()
+    is_u8 = (input.dtype == np.uint8) if as_numpy else (input.dtype == torch.uint8)
+    if not is_u8:
+        kind = input.dtype.kind if as_numpy else ("i" if not (input.dtype.is_floating_point or input.dtype == torch.bool) else "f")
+        if kind not in ("i", "u"):
+            raise TypeError("simt_b200.label_mapping takes integer images")
+        xt = torch.from_numpy(np.ascontiguousarray(input).astype(np.int64)) if as_numpy else input
+        out = _label_mapping_generic(xt.to(dev), [(int(a), int(b)) for a, b in np.asarray(mapping).tolist()])
+        return out.cpu().numpy() if as_numpy else out
     shape = tuple(input.shape)
     x = _to_dev(input, dev)
     lut = torch.from_numpy(build_lut(mapping)).to(dev)

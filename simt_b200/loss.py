@@ -43,6 +43,23 @@ class _NLL2dFn(torch.autograd.Function):
         return dprob, None, None
 
 
+def _weighted_ce2d(predict, target, weight, ignore_label, is_softmax):
+    """``CrossEntropy2d.forward(..., weight=w)`` (utils/loss.py:14,36,39): per-class weights, weighted-mean reduction
+    (sum_i w[y_i] l_i / sum_i w[y_i], what ``F.cross_entropy`` / ``F.nll_loss(weight=)`` compute).  No call site of the
+    reference passes ``weight``, so this rare form is composed from stock torch ops on the tensors' own device (for
+    CUDA tensors: torch's CUDA kernels; nothing here runs on the host) instead of a dedicated kernel: the log-probability
+    of the label is gathered per pixel, never a [N_valid, C] copy like the reference's boolean-mask gather."""
+    valid = (target >= 0) & (target != ignore_label)
+    y = torch.where(valid, target, torch.zeros_like(target)).long()
+    if is_softmax:
+        logp = torch.log_softmax(predict, dim=1)
+    else:
+        logp = torch.log(predict)
+    picked = logp.gather(1, y.unsqueeze(1)).squeeze(1)                  # [n, h, w]
+    wy = weight.to(device=predict.device, dtype=predict.dtype)[y] * valid.to(predict.dtype)
+    return -(wy * torch.where(valid, picked, torch.zeros_like(picked))).sum() / wy.sum()
+
+
 class CrossEntropy2d(nn.Module):
     """Masked 2-d cross entropy; mirrors utils/loss.py:6-40 of the reference.
 
@@ -50,7 +67,8 @@ class CrossEntropy2d(nn.Module):
     resize and T = I).  ``is_softmax=False``: ``predict`` holds probabilities, the loss is
     ``-mean log predict[y]`` over valid pixels (``Tseg_loss`` at tools/trainV2_simt.py:304,408-409).
     Valid = ``target >= 0`` and ``target != ignore_label``; mean over valid pixels; all-ignored
-    gives NaN like the reference.  CUDA only.
+    gives NaN like the reference.  ``weight`` (per-class, weighted mean; unused by the reference's callers) takes a
+    torch-op composition on the device instead of the fused kernels.  CUDA only.
     """
 
     def __init__(self, size_average=True, ignore_label=255, is_softmax=True):
@@ -66,11 +84,10 @@ class CrossEntropy2d(nn.Module):
         assert predict.size(0) == target.size(0), "{0} vs {1} ".format(predict.size(0), target.size(0))
         assert predict.size(2) == target.size(1), "{0} vs {1} ".format(predict.size(2), target.size(1))
         assert predict.size(3) == target.size(2), "{0} vs {1} ".format(predict.size(3), target.size(2))
-        if weight is not None:
-            raise NotImplementedError("simt_b200.CrossEntropy2d: per-class `weight` is not on the accelerated path "
-                                      "(no call site in the reference passes it)")
         if not predict.is_cuda:
             raise RuntimeError("simt_b200.CrossEntropy2d runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if weight is not None:
+            return _weighted_ce2d(predict, target, weight, self.ignore_label, self.is_softmax)
         if target.dtype not in (torch.uint8, torch.int64):
             target = target.long()
         if predict.dtype != torch.float32:

@@ -353,3 +353,26 @@ def test_plain_ce_huge_margin_is_finite_like_log_softmax(gap):
     assert np.isfinite(float(loss)) and np.isfinite(dl).all()
     assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
     _check(dl, lg.grad.numpy(), "dlogits")
+
+
+@pytest.mark.parametrize("is_softmax", [True, False])
+def test_cross_entropy_2d_per_class_weight(is_softmax):
+    """CrossEntropy2d(...)(predict, target, weight=w) (utils/loss.py:14,36,39): weighted mean over valid pixels."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 19, 24, 40, generator=g)
+    if not is_softmax:
+        x = torch.softmax(x, dim=1)
+    y = torch.randint(0, 19, (2, 24, 40), generator=g)
+    y[torch.rand(2, 24, 40, generator=g) < 0.2] = 255
+    w = torch.rand(19, generator=g) + 0.1
+    xr = x.clone().requires_grad_(True)
+    ref = O.cross_entropy_2d(xr, y, is_softmax=is_softmax, weight=w)
+    ref.backward()
+    dev = torch.device("cuda")
+    xg = x.to(dev).requires_grad_(True)
+    loss = simt_b200.CrossEntropy2d(is_softmax=is_softmax)(xg, y.to(dev), weight=w.to(dev))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    _check(xg.grad.cpu().numpy(), xr.grad.numpy(), "d predict (weighted)")

@@ -211,3 +211,16 @@ def test_eval_argmax_shapes_vs_oracle(sa, sb, size):
     top2 = z.topk(2, dim=1).values
     near_tie = ((top2[:, 0] - top2[:, 1]) < 1e-4).numpy()
     assert not ((got != ref) & ~near_tie).any()
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int32, np.int64])
+def test_label_mapping_integer_images(dtype):
+    """label_mapping takes any integer array (tools/compute_iou.py:18-22), not only the uint8 PNG images."""
+    import simt_b200
+    from oracle import simt_oracle as O
+    rng = np.random.default_rng(8)
+    m = np.array(O.CITYSCAPES_LABEL2TRAIN)
+    x = rng.integers(-1, 40, size=(61, 47)).astype(dtype)
+    got = simt_b200.label_mapping(x, m)
+    ref = O.label_mapping(x, m)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)

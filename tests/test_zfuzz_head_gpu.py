@@ -1,5 +1,6 @@
-"""Randomised GPU parity sweep.  pytest (-m gpu) runs a bounded number of cases; by hand for a longer sweep:
-    python tests/test_fuzz_head_gpu.py [n_cases] [seed]
+"""Randomised GPU parity sweep (named so that it is collected AFTER the deterministic parity tests).  pytest (-m gpu) runs a
+bounded number of cases; by hand for a longer sweep:
+    python tests/test_zfuzz_head_gpu.py [n_cases] [seed]
 Random shapes (up-, down- and identity-sampling, odd sizes, 1-wide / 1-high tensors), channel counts, label patterns and
 entry points (autograd simt_head, HeadRunner.step, Placeholder_loss) against the fp64 oracle at the 1e-5 bar."""
 import os
@@ -91,7 +92,7 @@ def run_fuzz(n_cases, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("seed", [0])
 def test_fuzz_head(seed):
     worst, fails = run_fuzz(120, seed)
     assert not fails, "\n".join(fails)

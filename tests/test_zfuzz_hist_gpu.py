@@ -1,5 +1,5 @@
 """Randomised GPU sweep of the integer histograms against numpy.  pytest (-m gpu) runs a bounded number of cases;
-by hand for a longer sweep:  python tests/test_fuzz_hist_gpu.py [n_cases] [seed]
+by hand for a longer sweep:  python tests/test_zfuzz_hist_gpu.py [n_cases] [seed]
 Random sizes (0 .. 6 M pixels, ragged tails), misaligned views, uint8 / int64 inputs, value ranges that include
 out-of-range ground truth (masked like the reference) and the three arities of fast_hist; bit-exact or bust."""
 import os
@@ -64,7 +64,7 @@ def run_fuzz(n_cases, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("seed", [0])
 def test_fuzz_hist(seed):
     fails = run_fuzz(100, seed)
     assert not fails, "\n".join(fails)
