@@ -120,8 +120,11 @@ __global__ void __launch_bounds__(256) head_prep_kernel(float* __restrict__ dlog
   }
 }
 
-// Sharded, deferred mode: finish everything that is outstanding now (HeadRunner.finish()): the older pending step, then
-// the last step (whose stats may not even have left this rank yet: no fused kernel ran since).  Collective in spirit:
+// Sharded, deferred mode: finish everything that is outstanding now (HeadRunner.finish()).  ORDER: first the pending
+// steps (oldest first), THEN push the last step's stats (which may not have left this rank yet: no fused kernel ran
+// since) and reduce it.  A rank may overwrite its peers' copies of stats(u - 2) with stats(u) only after it has read
+// every peer's stats(u - 1) -- a peer pushes those only after it has finished reading stats(u - 2)
+// (tests/test_xchg_protocol_cpu.py checks this order, and that the opposite one loses words).  Collective in spirit:
 // the peers' stats of the last step only arrive once they run their next step or this kernel.
 __global__ void __launch_bounds__(256) head_finish_kernel(unsigned long long* __restrict__ ws, const XchgArgs X,
                                                            const FinishArgs F) {
@@ -129,12 +132,14 @@ __global__ void __launch_bounds__(256) head_finish_kernel(unsigned long long* __
   const unsigned long long p0 = *reinterpret_cast<volatile unsigned long long*>(ws + WS_PENDING);
   const unsigned long long p1 = *reinterpret_cast<volatile unsigned long long*>(ws + WS_PENDING_ODD);
   const unsigned long long unsent = *reinterpret_cast<volatile unsigned long long*>(ws + WS_UNSENT);
-  if (unsent != 0ULL) push_stats_value(X, reinterpret_cast<const double*>(ws + kWsHeader / 8), F.C, F.CKP, unsent, i);
-  // oldest first, so that the outputs end up holding the latest step
-  unsigned long long todo[3] = {p0, p1, unsent};
+  unsigned long long todo[2] = {p0, p1};
   if (todo[0] > todo[1]) { const unsigned long long t = todo[0]; todo[0] = todo[1]; todo[1] = t; }
-  for (int q = 0; q < 3; ++q)
+  for (int q = 0; q < 2; ++q)
     if (todo[q] != 0ULL) finish_pending(X, F, todo[q], i);
+  if (unsent != 0ULL) {
+    push_stats_value(X, reinterpret_cast<const double*>(ws + kWsHeader / 8), F.C, F.CKP, unsent, i);
+    finish_pending(X, F, unsent, i);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();

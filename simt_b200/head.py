@@ -236,6 +236,7 @@ class HeadRunner:
         self._graphs = {}
         self._graph_keepalive = []
         self._checked = set()
+        self._deferred = False      # sharded, pipelined mode: a deferred step is outstanding
         # sharded: the exchanges are fused into the step's kernels over CUDA-IPC peer memory when every rank can map
         # every other rank's mailbox (one node); otherwise one library all-reduce per step
         self.mailbox = None
@@ -356,6 +357,11 @@ class HeadRunner:
                 return self.loss, dl_t, self.dT
             if self._world > 1:
                 mb = self.mailbox
+                if not defer and self._deferred:
+                    # a synchronous step pushes its stats at once: every deferred step must have been reduced first
+                    # (protocol invariant, tests/test_xchg_protocol_cpu.py); every rank takes this branch together
+                    self.finish()
+                self._deferred = bool(defer)
                 self._grad_out = grad_out
                 rc = self.lib.simt_head_step_sharded(logits.data_ptr(), B, CK, h, w, tp, C, labels.data_ptr(),
                                                      self.label_bytes, H, W, self.ignore, gp, dl, dT, stats, loss, err,
@@ -386,6 +392,7 @@ class HeadRunner:
                                                    mb.rank, mb.world, mb.ptrs, _stream_ptr())
         if rc:
             _lib.check(rc, "simt_head_finish_sharded")
+        self._deferred = False
         return self.loss, self.dT
 
     def graph_step(self, logits, T, labels, grad_out=None, next_labels=None, defer=False, out=None):
@@ -396,6 +403,8 @@ class HeadRunner:
         collective inside the graph); with the all-reduce fallback they take the eager path."""
         if self._world > 1 and self.mailbox is None:
             return self.step(logits, T, labels, grad_out, out=out)
+        if self._world > 1 and not defer and self._deferred:
+            self.finish()                                    # (see step(): a synchronous step drains the deferred ones)
         key = (logits.data_ptr(), None if T is None else T.data_ptr(), labels.data_ptr(),
                None if grad_out is None else grad_out.data_ptr(),
                None if next_labels is None else next_labels.data_ptr(), bool(defer), None if out is None else out.data_ptr())
@@ -413,6 +422,8 @@ class HeadRunner:
             self._graphs[key] = g
             self._graph_keepalive.append((logits, T, labels, grad_out, next_labels, out))
         g.replay()
+        if self._world > 1:
+            self._deferred = bool(defer)
         return self.loss, (self.dlogits if out is None else out), self.dT
 
     def global_loss(self):
