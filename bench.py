@@ -440,6 +440,7 @@ def sharded_parity(dist, rank, world, dev, T, runner, lg, lab, global_inputs, pi
                "what": "sharded step vs the same global batch through the one-GPU step on rank 0 (rank 0's dLogits slice)"}
         out["ok"] = bool(out["loss_rel"] <= 1e-5 and out["dT_rel"] <= 1e-5 and out["dlogits_rel"] <= 1e-5 and bitwise)
         one.close()
+    dist.barrier()       # rank 0's extra work is waited for on the host, not inside the next step's bounded in-kernel wait
     return out
 
 

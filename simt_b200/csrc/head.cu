@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
 #pragma unroll
       for (int q = 0; q < kFinSlices; ++q) t += sm[q][tx];
       const int y = o / CKP, k = o - y * CKP;
+      sm[0][tx] = -t;   // column tx is read by this thread only: the block's other warps push this value below
       if (k < CK) {
         if (stats) stats[2 + k * C + y] = -t;
         if (defer) reinterpret_cast<double*>(ws + kWsHeader / 8)[2 + k * C + y] = -t;   // staging: awaits its push
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
     const bool mine = o < ndt && k < CK;
     const int i = 2 + k * C + y;     // index in the caller's stats buffer; the slot keeps the tile order (entry 2 + o)
     if (mine && ty < X.world && !defer)
-      ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.slot_entries), 2 + o, seq, stats[i]);
+      ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.slot_entries), 2 + o, seq, sm[0][tx]);   // (not stats[i]: warp 0 overwrites it)
     if (mine && ty == 0 && !defer) {
       double t = 0.0;
       bool ok = true;
