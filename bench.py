@@ -169,7 +169,7 @@ def cpu_reference_step(O, ce, lg, T, lab64):
     Tt = T.clone().requires_grad_(True)
     loss = O.simt_head_loss(lgi, Tt, lab64, (H, W), ce=ce)
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
 
 def _ref_sample_text(kind, cores):
@@ -521,6 +521,10 @@ def run_ours(args, rank, local_rank, world):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
         group = dist.group.WORLD
+        # in-kernel waits for a peer give up after ~2 s here (library default ~12 s): the ranks of this loop never drift
+        # further apart than a graph capture, and a box whose peer mapping does not work is then found by the guard
+        # below within seconds (NaN outputs + error bit, never a hang)
+        lib.simt_xchg_set_timeout(1 << 21)
 
     n_sets = 12          # 12 x (5.1 MB logits + 4.2 MB labels + 5.1 MB dLogits) = 173 MB > 126 MB L2
     sets = make_inputs(n_sets, 1234 + 1000 * rank, device=dev)
@@ -593,6 +597,13 @@ def run_ours(args, rank, local_rank, world):
             barrier()
     for i in range(max(args.warmup, 3, n_sets)):   # every buffer set captures its graph here
         gstep(i)
+    barrier()
+    if world > 1:
+        bad = simt_b200.head.error_flag(dev).clone().to(torch.int32)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) != 0:
+            raise RuntimeError(f"bench.py: a rank flagged error bits {int(bad.item())} during the graph warm-up "
+                               "(SIMT_ERRBIT_*, include/simt_b200.h); not timing a broken exchange")
     ms = timed(gstep, args.steps)
     labeled = sum(labeled_per_set[i % n_sets] for i in range(args.steps))
     # a second, 100x longer look at the same loop (the K-step region above lasts ~2 ms)
@@ -780,6 +791,8 @@ def main():
     if args.impl == "reference":
         if args.steps > 60:      # the CPU arm costs ~0.7 s per full-batch step: keep a default run within minutes
             args.steps = 60
+        if args.warmup > 5:
+            args.warmup = 5
         run_reference_arm(args, rank)
         return
     if world == 1 and args.gpus > 1:

@@ -318,6 +318,13 @@ int simt_eval_argmax(const float* logits_a, int CKa, int ha, int wa, const float
  * production access pattern but skip the counting, so the histogram they return is meaningless -- never leave it on. */
 void simt_hist_set_tuning(int mode, int warps_per_cta, int unroll);
 
+/* test hook, HOST ONLY (no GPU needed): the pixel -> cell tables the kernels derive for one axis of the
+ * align_corners=True bilinear resize in -> out (torch ATen/native/UpSample.h:271-296,442-476), from
+ * the same host/device functions the kernels call (csrc/common.cuh).  Pixel X reads sources cell[X] and
+ * min(cell[X] + 1, in - 1) with weights 1 - lambda[X] and lambda[X]; first_px[c] (n_cells + 1 entries, n_cells =
+ * max(in - 1, 1)) is the first pixel of cell c.  tests/test_index_math_cpu.py compares them with torch's own weights. */
+int simt_debug_resize_tables(int in, int out, int* cell, float* lambda, int* first_px);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,7 @@ SIGNATURES = {
     "simt_xchg_close": (c_int, [c_void_p]),
     "simt_xchg_destroy": (c_int, [c_void_p]),
     "simt_xchg_set_timeout": (None, [c_longlong]),
+    "simt_debug_resize_tables": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "simt_head_step_sharded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                        c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                        c_int, c_int, ctypes.POINTER(c_void_p), c_void_p, c_int, c_void_p]),

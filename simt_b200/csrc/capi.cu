@@ -87,4 +87,17 @@ int simt_b200_profile_read(double* total_ms, long long* launches) {
   return 0;
 }
 
+int simt_debug_resize_tables(int in, int out, int* cell, float* lambda, int* first_px) {
+  if (in <= 0 || out <= 0 || !cell || !lambda || !first_px) return SIMT_EINVAL;
+  // exactly make_plan()'s scale / cell count (head.cu) and the tables head_kernel builds in its prologue
+  const float scale = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const int ncell = in > 1 ? in - 1 : 1;
+  for (int X = 0; X < out; ++X) {
+    cell[X] = cell_of(X, scale, ncell);
+    lambda[X] = lambda_of(X, scale, cell[X]);
+  }
+  for (int c = 0; c <= ncell; ++c) first_px[c] = first_px_of_cell(c, scale, ncell, out);
+  return 0;
+}
+
 }  // extern "C"
