@@ -13,6 +13,7 @@ The simulator replays the protocol's reads / writes as the kernels issue them:
                        finalize : leaves stats(s) unsent
   finish               reduce what is pending (oldest first), THEN push what is unsent and reduce it
   A synchronous step on a runner with deferred steps outstanding is preceded by finish (HeadRunner does that).
+  "announce_sync": synchronous stats with announced next labels (step(next_labels=..., defer=False)).
 The invariant behind the order: a rank pushes stats(u) -- overwriting every peer's copy of its stats(u - 2) -- only after
 it has read stats(u - 1) of all peers, and a peer only pushes stats(u - 1) after it has finished reading stats(u - 2).
 
@@ -135,7 +136,10 @@ class Sim:
                 raise Violation(f"rank {rk.r}: counts of step {s} read {got}")
 
         if not pipelined:
-            yield from acquire()
+            if rk.count_next is not None:                     # synchronous stats, but the next labels were announced
+                yield from self.join([cta0_push(), acquire()])
+            else:
+                yield from acquire()
         elif self.two_cta:                                    # the earlier form: three concurrent sub-actors
             subs = [cta0_push(), cta0_finish(), acquire()]
             yield from self.join(subs)
@@ -189,7 +193,7 @@ class Sim:
     def rank_program(self, rk):
         for s in range(1, self.steps + 1):
             pipelined = self.mode == "pipelined" or (self.mode == "mixed" and s % 3 != 0)
-            next_known = pipelined and self.announce and s < self.steps
+            next_known = (pipelined or self.mode == "announce_sync") and self.announce and s < self.steps
             if not pipelined and (rk.unsent or any(rk.pending)):
                 yield from self.finish_kernel(rk)             # HeadRunner: a synchronous step drains the deferred ones first
             yield from self.prologue(rk, s, next_known)
@@ -228,7 +232,7 @@ class Sim:
 
 
 @pytest.mark.parametrize("n", [2, 3, 4, 8])
-@pytest.mark.parametrize("mode", ["sync", "pipelined", "mixed"])
+@pytest.mark.parametrize("mode", ["sync", "pipelined", "mixed", "announce_sync"])
 def test_protocol_never_loses_a_word(n, mode):
     for seed in range(60):
         Sim(n, steps=9, mode=mode, rng=random.Random(1000 * n + seed)).run()
