@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import make_ref, simt_oracle as O  # noqa: E402
 
+make_ref.make(verbose=False)   # a no-op where /root/reference does not exist (GPU box): oracle/_ref then travels with the tree
 CE, CIOU = make_ref.load()
 pytestmark = pytest.mark.skipif(CE is None, reason="oracle/_ref not made (no /root/reference here)")
 
