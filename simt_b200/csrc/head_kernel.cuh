@@ -45,29 +45,9 @@
 #include <mutex>
 #include <type_traits>
 #pragma once
-#include "xchg.cuh"
+#include "step_xchg.cuh"
 
 namespace simt {
-
-// MODE_STEP: forward + backward with the 1/N_valid scale known ON THE DEVICE before the kernel starts (a label-only
-// count pass), so dLogits leave the kernel final and there is no scale pass.  Single GPU only: sharded, the count
-// would be a second rendezvous per step on top of the stats exchange (measured slower than scaling after ONE exchange).
-// MODE_STEPX: MODE_STEP on one rank's shard of the batch (the prologue talks to the peers' mailboxes); its own
-// instantiation, so that the single-GPU kernel carries none of that code.
-enum { MODE_FWD = 0, MODE_FWDBWD = 1, MODE_BWD = 2, MODE_PLACE = 3, MODE_STEP = 4, MODE_STEPX = 5 };
-
-static constexpr float kLog2e = 1.4426950408889634f;
-static constexpr double kLn2 = 0.6931471805599453094;
-
-// What the kernels that FINISH a sharded step write (the all-reduced results of that step).
-struct FinishArgs {
-  double* stats;        // [2 + CK*C]
-  float* loss_mean;
-  float* dT;            // [CK*C] or null
-  const float* grad_out;
-  int* err;
-  int CK, C, CKP;       // CKP: row length of the kernel's dT tile (the order the values travel in)
-};
 
 struct HeadArgs {
   const float* logits;
@@ -249,98 +229,6 @@ struct LabelFetch<long long> {
   }
 };
 
-// Workspace header (the first kWsHeader bytes of the caller's workspace), u64 words:
-//   [0] unit scheduler counter  [1] count accumulator  [2] prep ticket  [3] count_local (f64)  [4] finalize ticket
-//   [5] count_global (f64, sharded)  [6], [10] pending steps of even / odd parity: stats pushed, reduction outstanding
-//   (sharded, deferred mode)  [7] count accumulator of next_labels  [8] unsent step: local stats not pushed yet
-//   [9] tagged count word of the next step, to be pushed by the fused kernel
-enum { WS_COUNTER = 0, WS_ACCUM = 1, WS_TICKET = 2, WS_COUNT_LOCAL = 3, WS_FIN_TICKET = 4, WS_COUNT_GLOBAL = 5,
-       WS_PENDING = 6, WS_ACCUM_NEXT = 7, WS_UNSENT = 8, WS_COUNT_NEXT = 9, WS_PENDING_ODD = 10 };
-__host__ __device__ __forceinline__ int ws_pending_word(unsigned long long step) { return (step & 1ULL) ? WS_PENDING_ODD : WS_PENDING; }
-static constexpr size_t kWsHeader = 128;
-
-// slot entry of value i of the caller's stats buffer: {loss, count} first, then dT[k][y] at 2 + y * CKP + k (the
-// kernel's tile order: a warp's 32 values are contiguous)
-__device__ __forceinline__ int stats_slot_entry(int i, int C, int CKP) {
-  if (i < 2) return i;
-  const int k = (i - 2) / C, y = (i - 2) - k * C;
-  return 2 + y * CKP + k;
-}
-// push value i of this rank's local stats (step `seq`) into slot [parity][rank] of every mailbox
-__device__ __forceinline__ void push_stats_value(const XchgArgs& X, const double* stats, int C, int CKP,
-                                                 unsigned long long seq, int i) {
-  if (i >= X.n_stats) return;
-  const double v = stats[i];
-  const int e = stats_slot_entry(i, C, CKP);
-  for (int r = 0; r < X.world; ++r) ll_push_f64(slot_of(X.mail[r], (int)(seq & 1ULL), X.rank, X.slot_entries), e, seq, v);
-}
-
-// Sharded, deferred mode: the stats of step `pend` were pushed by every rank (from the prologue of its next fused
-// kernel, or by its head_finish_kernel); wait for them in this rank's mailbox, sum in rank order (bitwise identical on
-// every rank), write loss / dT / stats.  Value i of the caller's stats buffer.
-// A peer that never arrives poisons the outputs with NaN and raises SIMT_ERRBIT_XCHG_TIMEOUT.
-__device__ __forceinline__ void finish_pending(const XchgArgs& X, const FinishArgs& F, unsigned long long pend, int i) {
-  if (i >= X.n_stats) return;
-  unsigned char* own = X.mail[X.rank];
-  const int par = (int)(pend & 1ULL);
-  const int e = stats_slot_entry(i, F.C, F.CKP);
-  // first look: every word of every rank in flight at once (they arrived long ago in the pipelined schedule)
-  unsigned long long wv[kMaxPeers][2], wc[kMaxPeers][2];
-#pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r)
-    if (r < X.world) {
-      const unsigned long long* sl = slot_of(own, par, r, X.slot_entries);
-      wv[r][0] = ld_relaxed_sys(sl + 2 * e); wv[r][1] = ld_relaxed_sys(sl + 2 * e + 1);
-      wc[r][0] = ld_relaxed_sys(sl + 2); wc[r][1] = ld_relaxed_sys(sl + 3);
-    }
-  const unsigned long long tag = pend & 0xffffffffULL;
-  double t = 0.0, cnt = 0.0;
-  bool ok = true;
-#pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r)
-    if (r < X.world) {
-      double v, c;
-      if ((wv[r][0] >> 32) == tag && (wv[r][1] >> 32) == tag && (wc[r][0] >> 32) == tag && (wc[r][1] >> 32) == tag) {
-        v = __longlong_as_double((long long)((wv[r][1] << 32) | (wv[r][0] & 0xffffffffULL)));
-        c = __longlong_as_double((long long)((wc[r][1] << 32) | (wc[r][0] & 0xffffffffULL)));
-      } else {   // not there yet: poll
-        v = c = 0.0;
-        ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), e, pend, X.max_spins, &v) && ok;
-        ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), 1, pend, X.max_spins, &c) && ok;
-      }
-      t += v;
-      cnt += c;
-    }
-  const float poison = nanf("");
-  if (!ok && F.err) atomicOr(F.err, SIMT_ERRBIT_XCHG_TIMEOUT);
-  if (F.stats) F.stats[i] = ok ? t : (double)poison;
-  if (i >= 2 && F.dT && i - 2 < F.CK * F.C)
-    F.dT[i - 2] = ok ? (float)(t * ((F.grad_out ? (double)__ldg(F.grad_out) : 1.0) / cnt)) : poison;
-  if (i == 0 && F.loss_mean) {
-    float m = (float)(t / cnt);   // 0/0 -> NaN like the reference's mean over nothing
-    if (!ok || (F.err && (*F.err & SIMT_ERRBIT_LABEL_RANGE))) m = poison;
-    *F.loss_mean = m;
-  }
-}
-
-// Sharded step: wait (bounded) for every rank's valid-pixel count in this rank's mailbox and return
-// grad_out / sum(counts); NaN + SIMT_ERRBIT_XCHG_TIMEOUT when a peer never arrives.  One thread per CTA, in the prologue.
-static __device__ __forceinline__ float acquire_global_scale(const XchgArgs& X, const float* grad_out, int* err,
-                                                             double* count_global, int lane) {
-  unsigned char* own = X.mail[X.rank];
-  const unsigned long long seq = step_seq(own);
-  unsigned long long n = 0ULL;
-  bool ok = true;
-  if (lane < X.world) ok = wait_count(count_slot_of(own, seq, lane), seq, X.max_spins, &n);   // one lane per rank
-  double c = (double)n;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);   // integers: any order is exact
-  ok = __all_sync(0xffffffffu, ok);
-  if (!ok && err && lane == 0) atomicOr(err, SIMT_ERRBIT_XCHG_TIMEOUT);
-  if (blockIdx.x == 0 && lane == 0 && count_global) *count_global = ok ? c : (double)nanf("");
-  return ok ? (float)((grad_out ? (double)__ldg(grad_out) : 1.0) / c) : nanf("");
-}
-
 static constexpr int kEdgeRows = 16;  // pixel rows per cell-row whose edge column is staged in smem
 
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB, bool IDENT>
@@ -395,47 +283,14 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   }
   if (MODE == MODE_STEP && tid == 0)   // the valid-pixel count was produced by head_prep_kernel before this launch
     s_gs = (float)((A.grad_out ? (double)__ldg(A.grad_out) : 1.0) / *A.count_local);
-  if (MODE == MODE_STEPX && tid < 32) {
-    // sharded step: the GLOBAL count = the sum of the ranks' counts, pushed into this rank's mailbox by the peers;
-    // a peer that never arrives poisons the gradients with NaN, never a partial sum
-    const float g = acquire_global_scale(A.X, A.grad_out, A.err, A.count_global, tid);
-    if (tid == 0) s_gs = g;
-  }
+#include "stepx_acquire.inc"   // MODE_STEPX: warp 0 acquires the ranks' valid counts
   for (int i = tid; i <= A.ncx; i += NT) xs_tab[i] = first_px_of_cell(i, A.sx, A.ncx, A.W);
   for (int i = tid; i <= A.ncy; i += NT) ys_tab[i] = first_px_of_cell(i, A.sy, A.ncy, A.H);
 #ifdef SIMT_EXP_LXTAB
   for (int i = tid; i < A.W; i += NT) lx_tab[i] = lambda_of(i, A.sx, cell_of(i, A.sx, A.ncx));
   for (int i = tid; i < A.H; i += NT) ly_tab[i] = lambda_of(i, A.sy, cell_of(i, A.sy, A.ncy));
 #endif
-  if (MODE == MODE_STEPX && blockIdx.x == 0) {
-    // Sharded, pipelined mode (deferred all-reduce): CTA 0 settles this rank's accounts with its peers HERE, at the
-    // start of ~90 us of arithmetic (peer stores issued by the short kernels around this one would hold up their
-    // retirement).  The ORDER matters:
-    //   1. finish the step before the previous one: its stats were pushed by every rank a whole step ago; read them
-    //      out of this rank's mailbox (slots of this step's parity) and write loss / dT / stats;
-    //   2. only then push the previous step's local stats (left in the workspace's staging area by its finalize) and
-    //      the valid count of the NEXT step's labels.  The count is what lets a peer start its next fused kernel, whose
-    //      prologue overwrites the very slots read in 1. -- so it must not leave before 1. is complete.
-    unsigned long long* wsh = A.ws_hdr;
-    const unsigned long long seq = step_seq(A.X.mail[A.X.rank]);
-    const unsigned long long pend = *reinterpret_cast<volatile unsigned long long*>(wsh + ws_pending_word(seq));
-    if (pend != 0ULL && pend + 2ULL <= seq)
-      for (int i = tid; i < A.X.n_stats; i += NT) finish_pending(A.X, A.fin, pend, i);
-    __syncthreads();
-    const unsigned long long unsent = *reinterpret_cast<volatile unsigned long long*>(wsh + WS_UNSENT);
-    if (unsent != 0ULL)
-      for (int i = tid; i < A.X.n_stats; i += NT)
-        push_stats_value(A.X, reinterpret_cast<const double*>(wsh + kWsHeader / 8), C, CKP, unsent, i);
-    const unsigned long long cw = *reinterpret_cast<volatile unsigned long long*>(wsh + WS_COUNT_NEXT);
-    if (cw != 0ULL && tid < A.X.world)
-      st_relaxed_sys(count_slot_of(A.X.mail[tid], seq + 1ULL, A.X.rank), cw);
-    __syncthreads();
-    if (tid == 0) {
-      if (pend != 0ULL && pend + 2ULL <= seq) wsh[ws_pending_word(seq)] = 0ULL;
-      if (unsent != 0ULL) { wsh[ws_pending_word(unsent)] = unsent; wsh[WS_UNSENT] = 0ULL; }
-      wsh[WS_COUNT_NEXT] = 0ULL;
-    }
-  }
+#include "stepx_cta0.inc"      // MODE_STEPX: CTA 0 settles the deferred exchange of earlier steps
   unsigned smid;
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
   float* ct = A.part_dT + (size_t)(smid % (unsigned)A.ntiles) * C * CKP;  // this SM's dT tile in global memory (L2 resident)
