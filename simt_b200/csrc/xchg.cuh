@@ -13,7 +13,11 @@
 // polls the word itself -- no flag, no fence, one NVLink store latency per exchange.
 // Stats slots are double-buffered by step parity, count rows by step mod 4; see xchg.cu for why that is enough.
 #pragma once
+#ifdef SIMT_CPU_EMULATION
+#include "cuda_shim.h"   // tests/cpu_simt: the same device code run by a CPU SIMT emulator (test infrastructure)
+#else
 #include "common.cuh"
+#endif
 
 namespace simt {
 
@@ -42,6 +46,17 @@ static constexpr unsigned long long kCountMask = (1ULL << 40) - 1ULL;
 __device__ __forceinline__ unsigned long long count_word(unsigned long long seq, unsigned long long count) {
   return ((seq & 0xffffffULL) << 40) | (count & kCountMask);
 }
+#ifdef SIMT_CPU_EMULATION
+// emulator: the store joins the rank's outbox and arrives later, out of order; a load is a scheduling point
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  cpusimt::R->outbox.push_back(cpusimt::PendingStore{p, v});
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  const unsigned long long v = __atomic_load_n(p, __ATOMIC_RELAXED);
+  cpusimt::yield();
+  return v;
+}
+#else
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -50,6 +65,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+#endif
 // Wait for the count word of step `seq`; false when the bound expires.
 __device__ __forceinline__ bool wait_count(const unsigned long long* p, unsigned long long seq, long long max_spins,
                                            unsigned long long* count) {
