@@ -40,7 +40,11 @@ thread_local Rank* R = nullptr;
 using namespace simt;
 
 // ---- problem (small, odd sizes) -------------------------------------------------------------------------------------
-static constexpr int C = 4, CK = 5, CKP = 20;       // CKP: the (10, 2) instantiation's padded channel count
+#ifndef EMU_C        /* -DEMU_C=19 -DEMU_CK=19: the bench geometry (13 finalize blocks, 2 finish blocks) */
+#define EMU_C 4
+#define EMU_CK 5
+#endif
+static constexpr int C = EMU_C, CK = EMU_CK, CKP = 20;       // CKP: the (10, 2) instantiation's padded channel count
 static constexpr int NSTATS = 2 + CK * C;
 static constexpr int G = 3;                           // CTAs of the fused kernel (loss / count partials)
 static constexpr int NTILES = 2;                      // per-SM dT tiles

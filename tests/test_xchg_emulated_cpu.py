@@ -52,6 +52,11 @@ def emul_push_first():
     return _build("xchg_emul_bug", "-DSIMT_EMU_BUG_PUSH_FIRST")
 
 
+@pytest.fixture(scope="module")
+def emul_bench_geometry():
+    return _build("xchg_emul_c19", "-DEMU_C=19", "-DEMU_CK=19")
+
+
 def _run(exe, *args, env=None, timeout=400):
     e = dict(os.environ)
     e.update(env or {})
@@ -70,6 +75,14 @@ def test_real_exchange_code_is_bit_exact_on_every_rank(emul, mode, world):
 def test_synchronous_form_long_run_eight_ranks(emul):
     """what bench.py --gpus 8 runs: slot reuse over both parities and all four count rows, many times"""
     rc, out = _run(emul, 8, 40, "sync", 7)
+    assert rc == 0, out
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("mode", ["sync", "pipelined", "mixed"])
+def test_bench_geometry_19_channels(emul_bench_geometry, mode, world):
+    """C = CK = 19 as in bench.py: 13 finalize blocks, 363 stats values in 2 finish blocks, slots of 2 + 19 * 64 entries"""
+    rc, out = _run(emul_bench_geometry, world, 6, mode, 5)
     assert rc == 0, out
 
 
