@@ -44,7 +44,11 @@ using namespace simt;
 #define EMU_C 4
 #define EMU_CK 5
 #endif
-static constexpr int C = EMU_C, CK = EMU_CK, CKP = 20;       // CKP: the (10, 2) instantiation's padded channel count
+#ifndef EMU_CKP      /* row length of the kernel's dT tile: 20 for CK <= 20 (CPL 10 x LPR 2), 24 for CK <= 24 (12 x 2) */
+#define EMU_CKP 20
+#endif
+static constexpr int C = EMU_C, CK = EMU_CK, CKP = EMU_CKP;
+static_assert(CK <= CKP, "the dT tile holds CKP >= CK channels per row");
 static constexpr int NSTATS = 2 + CK * C;
 static constexpr int G = 3;                           // CTAs of the fused kernel (loss / count partials)
 static constexpr int NTILES = 2;                      // per-SM dT tiles
@@ -201,10 +205,13 @@ static void rank_main(Shared* S, int rank) {
   cpusimt::R = &emu;
   const bool fault = S->die_rank >= 0;
 
+  const bool single = S->world == 1;      // simt_head_step on one GPU: XchgArgs{} (world 0), MODE_STEP, no exchange at all
   XchgArgs X{};
-  for (int r = 0; r < S->world; ++r) X.mail[r] = S->mail[(size_t)r];
-  X.rank = rank; X.world = S->world; X.n_stats = NSTATS;
-  X.slot_entries = 2 + C * kXchgMaxCKP;
+  if (!single) {
+    for (int r = 0; r < S->world; ++r) X.mail[r] = S->mail[(size_t)r];
+    X.rank = rank; X.world = S->world; X.n_stats = NSTATS;
+    X.slot_entries = 2 + C * kXchgMaxCKP;
+  }
   // no fault injected: wait for ever (a lost word shows up as the watchdog's dead-lock); the negative controls and the
   // fault runs use the kernels' own bounded waits, so a lost word shows up as poison + error bit within seconds
   const char* spins = getenv("XCHG_EMUL_MAX_SPINS");
@@ -265,7 +272,9 @@ static void rank_main(Shared* S, int rank) {
           *reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]), L.count);
     if (emu.rng() % 2) usleep((useconds_t)(emu.rng() % 200));
     EmuHeadArgs ha{X, &grad_out, &err, reinterpret_cast<double*>(&ws[WS_COUNT_GLOBAL]), ws.data(), F, gs.data()};
-    cpusimt::launch(G, NT, prologue_body, &ha);
+    if (!single) cpusimt::launch(G, NT, prologue_body, &ha);
+    else         // MODE_STEP (head_kernel.cuh): s_gs = grad_out / count_local
+      for (int g = 0; g < G; ++g) gs[(size_t)g] = (float)((double)grad_out / *reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]));
     {   // mirror of stepx_cta0.inc
       const unsigned long long pend = pending[s & 1];
       if (pend != 0 && pend + 2 <= (unsigned long long)s) { last_finished = pend; pending[s & 1] = 0; }
@@ -287,7 +296,7 @@ static void rank_main(Shared* S, int rank) {
     if (defer) unsent = (unsigned long long)s; else last_finished = (unsigned long long)s;
     CHECK(ws[WS_COUNTER] == 0ULL, "unit scheduler not re-armed");
     for (float v : tiles) CHECK(v == 0.f, "dT tiles not re-zeroed");
-    CHECK(*reinterpret_cast<volatile unsigned long long*>(X.mail[rank]) == (unsigned long long)s, "step counter");
+    if (!single) CHECK(*reinterpret_cast<volatile unsigned long long*>(X.mail[rank]) == (unsigned long long)s, "step counter");
     if (fault) {
       if (s >= S->die_step && S->mode == "sync") {      // a peer is gone: poison, never a partial sum
         CHECK((err & SIMT_ERRBIT_XCHG_TIMEOUT) != 0, "no timeout flagged (err %d)", err);
@@ -308,7 +317,7 @@ static void rank_main(Shared* S, int rank) {
   }
   if (!fault) {
     --s;
-    run_finish();                      // HeadRunner.finish() after the last step (a no-op kernel when nothing is outstanding)
+    if (!single) run_finish();         // HeadRunner.finish() after the last step (a no-op kernel when nothing is outstanding)
     check_outputs(true);
     CHECK(last_finished == (unsigned long long)S->steps, "last finished step %llu", last_finished);
     CHECK(err == 0, "error flag %d", err);

@@ -86,6 +86,22 @@ def test_bench_geometry_19_channels(emul_bench_geometry, mode, world):
     assert rc == 0, out
 
 
+def test_single_gpu_step_kernels(emul, emul_bench_geometry):
+    """world = 1: head_prep_kernel + head_finalize_kernel as simt_head_step launches them (no exchange): count, zeroing,
+    loss, dT scaled by grad_out / N on the device, tiles re-zeroed, scheduler re-armed"""
+    for exe in (emul, emul_bench_geometry):
+        rc, out = _run(exe, 1, 6, "sync", 3)
+        assert rc == 0, out
+
+
+def test_open_set_geometry_23_channels():
+    """K = 4 (BASELINE configs[2]): CK = 23 rows of T, dT tile rows of 24"""
+    exe = _build("xchg_emul_k4", "-DEMU_C=19", "-DEMU_CK=23", "-DEMU_CKP=24")
+    for world, mode in ((1, "sync"), (2, "sync"), (4, "mixed")):
+        rc, out = _run(exe, world, 5, mode, 3)
+        assert rc == 0, out
+
+
 @pytest.mark.parametrize("mode", ["sync", "pipelined", "mixed"])
 def test_a_dead_rank_poisons_the_survivors(emul, mode):
     rc, out = _run(emul, 4, 6, mode, 4, 2, 4)      # rank 2 stops before step 4
