@@ -426,6 +426,16 @@ class HeadRunner:
             self._deferred = bool(defer)
         return self.loss, (self.dlogits if out is None else out), self.dT
 
+    def error_word(self) -> torch.Tensor:
+        """The device's SIMT_ERRBIT_* word (int32[1], no synchronisation): copy it to the host alongside the loss, or call
+        ``check()`` at a point where a synchronisation is acceptable.  A sharded step whose peer never arrived has
+        already poisoned its loss / dT / dlogits with NaN when the bit is set."""
+        return self.err
+
+    def check(self) -> None:
+        """Synchronise and raise if a kernel flagged a contract violation or an exchange timeout (``check_errors``)."""
+        check_errors(self.dev)
+
     def global_loss(self):
         """loss over the all-reduced stats (sharded runs); a 0-dim f64 tensor, no sync."""
         return self.stats[0] / self.stats[1]
