@@ -56,6 +56,15 @@ WORKLOAD = (f"batch {B_PER_GPU}/GPU, logits {CK}x{h}x{w} -> {H}x{W} bilinear ali
 STRONG_B = 64
 
 
+N_SETS = 12          # rotating input / output sets per GPU: 12 x (5.1 MB logits + 4.2 MB labels + 5.1 MB dLogits) = 173 MB > 126 MB L2
+
+
+def bench_config(world):
+    """The `config` object of the JSON line -- the same for this arm and for `--impl reference` at the same --gpus."""
+    return {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"batch-sharded x{world}",
+            "l2": f"inputs and outputs rotate over {N_SETS} sets (173 MB per GPU) > 126 MB L2"}
+
+
 def alg_bytes_per_launch(B, ck=CK):
     """single-pass fwd+bwd = logits read + labels read + dLogits write."""
     return B * (4 * ck * h * w + H * W + 4 * ck * h * w)
@@ -172,12 +181,14 @@ def cpu_reference_step(O, ce, lg, T, lab64):
     return float(loss.detach())
 
 
-def _ref_sample_text(kind, cores):
+def _ref_sample_text(kind, cores, world=1):
     what = ("the reference's own CrossEntropy2d (oracle/_ref/loss.py, unmodified copy of utils/loss.py) under the "
             "restated composition of tools/trainV2_simt.py:371-372,402-409" if kind == "reference"
             else "oracle port of the reference's CPU PyTorch path")
-    return (f"all {B_PER_GPU} of {B_PER_GPU} images per step (the full batch of the same workload), {what}, "
-            f"torch {torch.__version__} CPU, {cores} threads")
+    part = (f"all {B_PER_GPU} of {B_PER_GPU} images per step (the full batch of the same workload)" if world <= 1 else
+            f"{B_PER_GPU} of the {B_PER_GPU * world} images of a global batch per step (one GPU's shard: a bounded sample "
+            f"of the same workload; labeled px/s on the CPU does not depend on the batch size)")
+    return f"{part}, {what}, torch {torch.__version__} CPU, {cores} threads"
 
 
 def run_cpu_baseline(budget_s=20.0):
@@ -221,12 +232,12 @@ def run_reference_arm(args, rank):
     dt = time.perf_counter() - t0
     labeled = int((lab != 255).sum())
     val = labeled * args.steps / dt
-    sample = _ref_sample_text(kind, cores)
+    sample = _ref_sample_text(kind, cores, max(args.gpus, 1))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "sample": sample},
+        "config": bench_config(max(args.gpus, 1)), "sample": sample,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -526,7 +537,7 @@ def run_ours(args, rank, local_rank, world):
         # below within seconds (NaN outputs + error bit, never a hang)
         lib.simt_xchg_set_timeout(1 << 21)
 
-    n_sets = 12          # 12 x (5.1 MB logits + 4.2 MB labels + 5.1 MB dLogits) = 173 MB > 126 MB L2
+    n_sets = N_SETS
     sets = make_inputs(n_sets, 1234 + 1000 * rank, device=dev)
     labeled_per_set = [int((lab != 255).sum()) for _, lab in sets]
     T = reference_T().to(dev)
@@ -723,10 +734,9 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": labeled_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"batch-sharded x{world}",
-                       "l2": f"inputs and outputs rotate over {n_sets} sets (173 MB per GPU) > 126 MB L2",
-                       "warmup_steps_run": 3 + max(args.warmup, 3, n_sets),
-                       "total_px_per_sec": B_PER_GPU * H * W * world * args.steps / (ms_max * 1e-3)},
+            "config": bench_config(world),
+            "warmup_steps_run": 3 + max(args.warmup, 3, n_sets),
+            "total_px_per_sec": B_PER_GPU * H * W * world * args.steps / (ms_max * 1e-3),
             "sustained": {"steps": sus_steps, "ms_per_step": sus_ms_max / sus_steps,
                           "value": labeled_all / args.steps * sus_steps / (sus_ms_max * 1e-3),
                           "what": "the same graph-replay loop over 100x the timed steps (barrier + sync both sides, max over ranks)"},
