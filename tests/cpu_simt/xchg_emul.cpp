@@ -158,6 +158,59 @@ static void finish_body(void* p) {
   head_finish_kernel(a->ws, a->X, a->F);
 }
 
+// ---- head_prep_kernel alone: label dtypes, alignments, sizes --------------------------------------------------------
+template <typename LabelT>
+struct PrepArgsT { float* dl; long long n_dl; const LabelT* lab; long long npix; int Cc; int ignore; unsigned long long* ws; };
+template <typename LabelT>
+static void prep_only_body(void* p) {
+  auto* a = (PrepArgsT<LabelT>*)p;
+  head_prep_kernel<LabelT>(a->dl, a->n_dl, a->lab, nullptr, a->npix, a->Cc, a->ignore, a->ws, XchgArgs{}, FinishArgs{});
+}
+static int prep_cases(unsigned long long seed) {
+  cpusimt::Rank emu;
+  emu.rng.seed(seed);
+  cpusimt::R = &emu;
+  std::mt19937_64 g(seed + 99);
+  int bad = 0;
+  for (int it = 0; it < 40; ++it) {
+    const long long npix = (long long)(g() % 3000);
+    const long long n_dl = (long long)(g() % 500);
+    const int off8 = (int)(g() % 17), offd = (int)(g() % 5);       // misaligned label / dLogits pointers
+    const int Cc = 1 + (int)(g() % 40);
+    const int ignore = (g() % 4 == 0) ? (int)(g() % 300) : 255;   // also ignore labels outside the uint8 range
+    const bool i64 = g() % 2;
+    std::vector<uint8_t> l8((size_t)npix + 64);
+    std::vector<long long> l64((size_t)npix + 8);
+    long long want = 0;
+    for (long long i = 0; i < npix; ++i) {
+      const long long v = i64 ? (long long)(g() % 300) - 20 : (long long)(g() % 256);
+      l8[(size_t)(off8 + i)] = (uint8_t)v; l64[(size_t)(off8 % 8 + i)] = v;
+      want += (v >= 0 && v < Cc && v != ignore);
+    }
+    std::vector<float> dl((size_t)n_dl + 8, 7.f);
+    std::vector<unsigned long long> ws(32, 0ULL);
+    const unsigned grid = 1 + (unsigned)(g() % 5), block = 32u * (1 + (unsigned)(g() % 8));
+    if (i64) {
+      PrepArgsT<long long> a{dl.data() + offd, n_dl, l64.data() + off8 % 8, npix, Cc, ignore, ws.data()};
+      cpusimt::launch(grid, block, prep_only_body<long long>, &a);
+    } else {
+      PrepArgsT<uint8_t> a{dl.data() + offd, n_dl, l8.data() + off8, npix, Cc, ignore, ws.data()};
+      cpusimt::launch(grid, block, prep_only_body<uint8_t>, &a);
+    }
+    const double got = *reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]);
+    bool ok = got == (double)want && ws[WS_ACCUM] == 0 && ws[WS_TICKET] == 0;
+    for (long long i = 0; i < n_dl; ++i) ok = ok && dl[(size_t)(offd + i)] == 0.f;
+    for (int i = 0; i < offd; ++i) ok = ok && dl[(size_t)i] == 7.f;                 // nothing outside the range is touched
+    for (size_t i = (size_t)(offd + n_dl); i < dl.size(); ++i) ok = ok && dl[i] == 7.f;
+    if (!ok) {
+      fprintf(stderr, "prep case %d: npix %lld n_dl %lld int64 %d C %d ignore %d grid %u block %u: count %g vs %lld\n", it, npix, n_dl,
+              (int)i64, Cc, ignore, grid, block, got, want);
+      ++bad;
+    }
+  }
+  return bad;
+}
+
 // ---- one emulated rank ----------------------------------------------------------------------------------------------
 struct Shared {
   int world, steps;
@@ -329,7 +382,12 @@ static void rank_main(Shared* S, int rank) {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 5) { fprintf(stderr, "usage: xchg_emul world steps mode seed [die_rank die_step]\n"); return 2; }
+  if (argc == 3 && std::string(argv[1]) == "prep") {
+    const int bad = prep_cases(strtoull(argv[2], nullptr, 10));
+    printf("%s prep: %d failed cases\n", bad ? "FAIL" : "OK", bad);
+    return bad ? 1 : 0;
+  }
+  if (argc < 5) { fprintf(stderr, "usage: xchg_emul world steps mode seed [die_rank die_step] | xchg_emul prep seed\n"); return 2; }
   Shared S;
   S.world = atoi(argv[1]); S.steps = atoi(argv[2]); S.mode = argv[3]; S.seed = strtoull(argv[4], nullptr, 10);
   if (argc >= 7) { S.die_rank = atoi(argv[5]); S.die_step = atoi(argv[6]); }

@@ -86,6 +86,14 @@ def test_bench_geometry_19_channels(emul_bench_geometry, mode, world):
     assert rc == 0, out
 
 
+def test_prep_kernel_label_dtypes_alignments_sizes(emul):
+    """head_prep_kernel alone: uint8 / int64 labels (negative and out-of-range values), ignore labels inside and outside
+    the uint8 range, misaligned label and dLogits pointers, empty and ragged sizes, several grid / block shapes"""
+    for seed in (1, 2, 3):
+        rc, out = _run(emul, "prep", seed)
+        assert rc == 0, out
+
+
 def test_single_gpu_step_kernels(emul, emul_bench_geometry):
     """world = 1: head_prep_kernel + head_finalize_kernel as simt_head_step launches them (no exchange): count, zeroing,
     loss, dT scaled by grad_out / N on the device, tiles re-zeroed, scheduler re-armed"""
