@@ -1,6 +1,13 @@
 // Shared helpers for the simt_b200 kernels (sm_100a only).
 #pragma once
+#ifdef SIMT_CPU_EMULATION
+// tests/cpu_simt: the device code of this library compiled with g++ against a CUDA-on-CPU shim (test infrastructure).
+// The shim supplies the CUDA built-ins and host versions of the inline-PTX helpers below; the host-side helpers that
+// call the CUDA runtime are left out.
+#include "cuda_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <math.h>
 #include <mutex>
@@ -10,6 +17,7 @@
 #error "simt_b200 is written for sm_100a (B200) only"
 #endif
 
+#ifndef SIMT_CPU_EMULATION
 #define SIMT_CUDA_TRY(expr)                     \
   do {                                          \
     cudaError_t e__ = (expr);                   \
@@ -63,6 +71,11 @@ inline int ensure_dynamic_smem(Kernel kernel, bool (&done)[64], int bytes) {
   return 0;
 }
 
+}  // namespace simt
+#endif  // !SIMT_CPU_EMULATION
+
+namespace simt {
+
 // ---- pixel <-> cell mapping, identical float arithmetic on host and device ----------
 __host__ __device__ __forceinline__ float src_index(float scale, int X) {
 #ifdef __CUDA_ARCH__
@@ -93,6 +106,7 @@ __host__ __device__ inline int first_px_of_cell(int c, float scale, int ncell, i
   return X;
 }
 
+#ifndef SIMT_CPU_EMULATION
 // launch profiler (capi.cu)
 bool prof_enabled();
 void prof_begin(cudaStream_t st);
@@ -122,5 +136,6 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
                : "l"(p));
   return r;
 }
+#endif  // !SIMT_CPU_EMULATION (the shim has host versions of ex2 / lg2 / rcp / ldg_stream)
 
 }  // namespace simt

@@ -117,6 +117,11 @@ __device__ __forceinline__ int group_min_i(int v) {
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2: two fp32 lanes per issue slot) ----
 // Operands are packed/unpacked with mov.b64 {lo, hi} inside the asm block (ptxas folds these into
 // register-pair allocation); reinterpret_cast of float2 references forces the values through local memory.
+#ifdef SIMT_CPU_EMULATION   /* tests/cpu_simt: the same arithmetic, one IEEE operation per component */
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#else
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 r;
   asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
@@ -144,10 +149,15 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return r;
 }
+#endif
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 // fire-and-forget 8-byte vector reduction (sm_90+): *(float2*)p += v, p 8-byte aligned
 __device__ __forceinline__ void red_add_v2(float* p, float2 v) {
+#ifdef SIMT_CPU_EMULATION
+  atomicAdd(p, v.x); atomicAdd(p + 1, v.y);
+#else
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
 }
 
 static constexpr float kPadLogit = -1.0e30f;  // padded channels: exp2 -> 0, no inf/NaN arithmetic
@@ -240,7 +250,11 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   constexpr int CKP = CPL * LPR;
   constexpr int CPW = 32 / LPR;  // cells per warp unit
   constexpr int NW = NT / 32;
+#ifdef SIMT_CPU_EMULATION
+  unsigned char* smem_raw = cpusimt::dynamic_smem();
+#else
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
   const int CK = A.CK, C = A.C;
   // [NW][4][NP][32] float2: the cell corners of every lane (log2 domain), re-read once per pixel row
   float2* Lsm = reinterpret_cast<float2*>(smem_raw);
@@ -292,7 +306,11 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 #endif
 #include "stepx_cta0.inc"      // MODE_STEPX: CTA 0 settles the deferred exchange of earlier steps
   unsigned smid;
+#ifdef SIMT_CPU_EMULATION
+  smid = blockIdx.x;
+#else
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
   float* ct = A.part_dT + (size_t)(smid % (unsigned)A.ntiles) * C * CKP;  // this SM's dT tile in global memory (L2 resident)
   __syncthreads();
 
@@ -840,12 +858,13 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
 // ------------------------------------------------------------------------------------------
 static constexpr int kMaxGridPerSm = 8;   // G = SM count * 8 bounds the grid (loss / count partials are per CTA)
 static constexpr int kMaxCKP = 64;
-extern std::mutex g_head_mutex;   // guards the tuning hook and the per-instantiation launch caches (head.cu)
-
 struct Plan {
   int CPL, LPR, NT, MINB, CKP;
   size_t smem;
 };
+
+#ifndef SIMT_CPU_EMULATION
+extern std::mutex g_head_mutex;   // guards the tuning hook and the per-instantiation launch caches (head.cu)
 
 template <int CPL, int LPR, int MODE, typename LabelT, int NT, int MINB, bool IDENT>
 static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
@@ -884,6 +903,8 @@ static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* gr
   return (int)cudaGetLastError();
 }
 
+#endif  // !SIMT_CPU_EMULATION
+
 // channel-count -> (CPL, LPR, threads, min CTAs/SM) instantiations
 #ifndef SIMT_MINB_BWD
 #define SIMT_MINB_BWD 3
@@ -902,6 +923,7 @@ static int launch_cfg(const HeadArgs& A, const Plan& P, cudaStream_t st, int* gr
   X(16, 4, 128, 3, 2)
 #endif
 
+#ifndef SIMT_CPU_EMULATION
 template <int MODE, typename LabelT, bool IDENT>
 static int dispatch(const HeadArgs& A, const Plan& P, cudaStream_t st, int* grid_out) {
 #define X(cpl, lpr, nt, minb_fwd, minb_bwd) \
@@ -937,5 +959,7 @@ static int dispatch_modes(int mode, int label_bytes, const HeadArgs& A, const Pl
   return dispatch<MODE_BWD, long long, IDENT>(A, P, st, grid_out);
 #endif
 }
+#endif  // !SIMT_CPU_EMULATION
 
 }  // namespace simt
+#include "head_plan.cuh"

@@ -13,11 +13,7 @@
 // polls the word itself -- no flag, no fence, one NVLink store latency per exchange.
 // Stats slots are double-buffered by step parity, count rows by step mod 4; see xchg.cu for why that is enough.
 #pragma once
-#ifdef SIMT_CPU_EMULATION
-#include "cuda_shim.h"   // tests/cpu_simt: the same device code run by a CPU SIMT emulator (test infrastructure)
-#else
-#include "common.cuh"
-#endif
+#include "common.cuh"   // (with SIMT_CPU_EMULATION: the CUDA-on-CPU shim of tests/cpu_simt)
 
 namespace simt {
 

@@ -29,10 +29,15 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint4 { unsigned x, y, z, w; };
 struct float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) float2 { float x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 
 namespace cpusimt {
 
@@ -61,6 +66,7 @@ struct Rank {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   std::vector<char*> stacks;    // reused from launch to launch
+  std::vector<unsigned char> dyn_smem;   // the running block's dynamic shared memory
   int cur = -1;                 // running fiber
   int live = 0;                 // fibers of the block that have not returned
   int bar_arrived = 0;
@@ -124,13 +130,22 @@ inline bool runnable(Rank* r, const Fiber& f) {
 
 static constexpr size_t kStackBytes = 32 * 1024;
 
-inline void launch(unsigned grid, unsigned block, void (*body)(void*), void* arg) {
+inline unsigned char* dynamic_smem() {
+  // 16-byte aligned start inside the block's buffer
+  unsigned char* p = R->dyn_smem.data();
+  return p + ((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15);
+}
+
+inline void launch(unsigned grid, unsigned block, void (*body)(void*), void* arg, size_t dyn_smem_bytes = 0) {
   Rank* r = R;
   while (r->stacks.size() < block) r->stacks.push_back(new char[kStackBytes]);
   r->body = body; r->body_arg = arg;
   r->gdim = Dim{grid, 1, 1}; r->bdim = Dim{block, 1, 1};
   for (unsigned b = 0; b < grid; ++b) {
     r->bid = Dim{b, 0, 0};
+    // shared memory starts out as garbage on the GPU: fill it with a NaN pattern so that a read of an unwritten word
+    // shows up in the results
+    r->dyn_smem.assign(dyn_smem_bytes + 16, (unsigned char)0xFF);
     r->fibers.assign(block, Fiber{});
     r->warps.assign((block + 31) / 32, Warp{});
     r->live = (int)block; r->bar_arrived = 0;
@@ -216,6 +231,55 @@ static inline T __shfl_xor_sync(unsigned, T v, int o) {
   memcpy(&r, &bits, sizeof(T));
   return r;
 }
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+  const int lane = cpusimt::my_lane();
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = bits; }
+  cpusimt::warp_barrier();
+  { cpusimt::Warp& w = cpusimt::my_warp(); bits = w.buf[src & 31]; }
+  cpusimt::warp_barrier();
+  T r;
+  memcpy(&r, &bits, sizeof(T));
+  return r;
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int delta) {
+  const int lane = cpusimt::my_lane();
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = bits; }
+  cpusimt::warp_barrier();
+  { cpusimt::Warp& w = cpusimt::my_warp(); bits = w.buf[lane >= delta ? lane - delta : lane]; }
+  cpusimt::warp_barrier();
+  T r;
+  memcpy(&r, &bits, sizeof(T));
+  return r;
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { cpusimt::warp_barrier(); }
+static inline bool __any_sync(unsigned, bool p) {
+  const int lane = cpusimt::my_lane();
+  { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = p ? 1ULL : 0ULL; }
+  cpusimt::warp_barrier();
+  bool any = false;
+  { cpusimt::Warp& w = cpusimt::my_warp(); for (int l = 0; l < cpusimt::warp_width(); ++l) any = any || (w.buf[l] != 0ULL); }
+  cpusimt::warp_barrier();
+  return any;
+}
+static inline int __reduce_max_sync(unsigned, int v) {
+  const int lane = cpusimt::my_lane();
+  { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = (unsigned long long)(long long)v; }
+  cpusimt::warp_barrier();
+  int m = v;
+  { cpusimt::Warp& w = cpusimt::my_warp(); for (int l = 0; l < cpusimt::warp_width(); ++l) { const int x = (int)(long long)w.buf[l]; m = x > m ? x : m; } }
+  cpusimt::warp_barrier();
+  return m;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31u));
+}
+static inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one OS thread per rank
 static inline bool __all_sync(unsigned, bool p) {
   const int lane = cpusimt::my_lane();
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = p ? 1ULL : 0ULL; }
@@ -237,4 +301,9 @@ static inline double __longlong_as_double(long long l) { double r; memcpy(&r, &l
 
 namespace simt {
 static inline uint4 ldg_stream_u4(const uint4* p) { return *p; }
+// host stand-ins for MUFU (ex2 / lg2 / rcp .approx.ftz): correctly rounded libm values instead of the ~2 ulp approximations
+static inline float ftz(float x) { return fabsf(x) < 1.17549435e-38f ? copysignf(0.f, x) : x; }
+static inline float ex2_approx(float x) { return ftz(exp2f(ftz(x))); }
+static inline float lg2_approx(float x) { x = ftz(x); return x == 0.f ? -INFINITY : log2f(x); }
+static inline float rcp_approx(float x) { return ftz(1.0f / ftz(x)); }
 }  // namespace simt

@@ -1,0 +1,148 @@
+// The fused head kernel itself on the CPU (TEST INFRASTRUCTURE ONLY; built as a shared library and driven through ctypes
+// by tests/test_head_emulated_cpu.py, no GPU).
+//
+// Compiles the UNMODIFIED csrc/head_kernel.cuh (the fused kernel, all modes), csrc/step_kernels.cuh (prologue,
+// finalize) and csrc/head_plan.cuh (the launch plan) with g++ against the CUDA-on-CPU shim (cuda_shim.h) and mirrors
+// the launch sequences of csrc/head.cu: run_head (simt_head_fwd / fwdbwd / bwd), run_step (simt_head_step) and
+// run_place (simt_placeholder_fwdbwd).  The inline-PTX helpers have host alternates behind SIMT_CPU_EMULATION
+// (fma.rn.f32x2 -> two fmaf, ex2/lg2/rcp.approx -> libm, red.global.add -> add, %smid -> block index); warps are 32
+// fibers, shuffles / votes / __syncwarp are barriers among them and the scheduler picks fibers at random, so lanes and
+// warps make progress in arbitrary order; dynamic shared memory starts out as a NaN pattern.
+#include <cstdio>
+#include <cstdlib>
+#include <unistd.h>
+
+#define SIMT_CPU_EMULATION 1
+#include "head_kernel.cuh"
+#include "step_kernels.cuh"
+
+namespace cpusimt {
+thread_local Rank* R = nullptr;
+[[noreturn]] void die(const char* what) {
+  fprintf(stderr, "EMULATION FAILURE: %s\n", what);
+  fflush(stderr);
+  _exit(3);
+}
+}  // namespace cpusimt
+
+using namespace simt;
+
+template <int CPL, int LPR, int MODE, typename L, int NT, int MINB, bool ID>
+static void kernel_body(void* p) { head_kernel<CPL, LPR, MODE, L, NT, MINB, ID>(*static_cast<const HeadArgs*>(p)); }
+
+// the instantiations the tests use: (10,2) for CK <= 20, (12,2) for CK <= 24, (10,4) for CK <= 40
+template <int MODE, typename L, bool ID>
+static int launch_mode(const HeadArgs& A, const Plan& P, unsigned grid) {
+  void (*body)(void*) = nullptr;
+  if (P.CPL == 10 && P.LPR == 2) body = kernel_body<10, 2, MODE, L, 128, 3, ID>;
+#ifndef HEAD_EMUL_SMALL
+  if (P.CPL == 12 && P.LPR == 2) body = kernel_body<12, 2, MODE, L, 128, 2, ID>;
+  if (P.CPL == 10 && P.LPR == 4) body = kernel_body<10, 4, MODE, L, 128, 3, ID>;
+#endif
+  if (!body) return SIMT_EUNSUPPORTED;
+  HeadArgs a = A;
+  cpusimt::launch(grid, (unsigned)P.NT, body, &a, P.smem);
+  return 0;
+}
+
+template <int MODE>
+static int launch_any(const HeadArgs& A, const Plan& P, unsigned grid, int label_bytes) {
+  if (MODE == MODE_PLACE) return launch_mode<MODE_PLACE, uint8_t, false>(A, P, grid);
+  const bool ident = A.T == nullptr;
+  if (label_bytes == 1) return ident ? launch_mode<MODE, uint8_t, true>(A, P, grid) : launch_mode<MODE, uint8_t, false>(A, P, grid);
+  return ident ? launch_mode<MODE, long long, true>(A, P, grid) : launch_mode<MODE, long long, false>(A, P, grid);
+}
+
+struct PrepA { float* dl; long long n_dl; const void* lab; long long npix; int C, ignore, label_bytes; unsigned long long* ws; };
+static void prep_body(void* p) {
+  PrepA* a = static_cast<PrepA*>(p);
+  if (a->label_bytes == 1)
+    head_prep_kernel<uint8_t>(a->dl, a->n_dl, static_cast<const uint8_t*>(a->lab), nullptr, a->npix, a->C, a->ignore, a->ws, XchgArgs{}, FinishArgs{});
+  else
+    head_prep_kernel<long long>(a->dl, a->n_dl, static_cast<const long long*>(a->lab), nullptr, a->npix, a->C, a->ignore, a->ws, XchgArgs{}, FinishArgs{});
+}
+struct FinA {
+  float* part_dT; const double* part_loss; const long long* part_cnt; int nparts, ntiles, CK, CKP, C, mode; float gscale;
+  unsigned long long* counter; double* stats; float* loss; float* dT; int* err; const float* grad_out; const double* count_dev;
+  unsigned long long* ws;
+};
+static void fin_body(void* p) {
+  FinA* a = static_cast<FinA*>(p);
+  head_finalize_kernel(a->part_dT, a->part_loss, a->part_cnt, a->nparts, a->ntiles, a->CK, a->CKP, a->C, a->mode, a->gscale, a->counter,
+                       a->stats, a->loss, a->dT, a->err, a->grad_out, a->count_dev, a->ws, XchgArgs{}, 0);
+}
+
+extern "C" {
+
+// mode: MODE_FWD 0, MODE_FWDBWD 1, MODE_BWD 2, MODE_PLACE 3, MODE_STEP 4 (csrc/step_xchg.cuh)
+// scale: MODE_BWD: the host-known grad_out / N; MODE_STEP: grad_out (the kernel divides by the counted N itself)
+// emulated device: sm_count SMs with ctas_per_sm resident CTAs; tune_ur / tune_rs as simt_head_set_tuning (0 = automatic)
+int emul_head(int mode, const float* logits, int B, int CK, int h, int w, const float* T, int C, const void* labels,
+              int label_bytes, int H, int W, int ignore, float scale, float place_thres, float place_lambda, float* dlogits,
+              double* stats, float* loss_mean, float* dT, int* err, int sm_count, int ctas_per_sm, int tune_ur, int tune_rs,
+              unsigned long long seed) {
+  if (!logits || B <= 0 || CK <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || sm_count <= 0 || ctas_per_sm <= 0) return SIMT_EINVAL;
+  if (mode != MODE_PLACE && (!labels || (label_bytes != 1 && label_bytes != 8))) return SIMT_EINVAL;
+  if (CK > kMaxCKP || C > 254) return SIMT_EUNSUPPORTED;
+  if (mode != MODE_PLACE && !T && C != CK) return SIMT_EINVAL;
+  cpusimt::Rank emu;
+  emu.rng.seed(seed);
+  cpusimt::R = &emu;
+
+  HeadArgs A{};
+  Plan P{};
+  A.logits = logits; A.T = (mode == MODE_PLACE) ? nullptr : T; A.labels = (mode == MODE_PLACE) ? nullptr : labels;
+  A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = (mode == MODE_PLACE) ? 255 : ignore;
+  A.gscale = (mode == MODE_BWD) ? scale : 1.f;
+  A.dlogits = dlogits; A.err = (mode == MODE_PLACE) ? nullptr : err;
+  A.place_thres = place_thres; A.place_lambda = place_lambda;
+  A.label_words_ok = (mode != MODE_PLACE && label_bytes == 1 && (reinterpret_cast<uintptr_t>(labels) & 3) == 0 &&
+                      (((long long)B * H * W) & 3) == 0) ? 1 : 0;
+  int rc = make_plan_for(mode == MODE_STEP ? MODE_STEP : mode, B, CK, C, h, w, H, W, PlanTuning{tune_ur, tune_rs, 0}, sm_count, &A, &P);
+  if (rc) return rc;
+  const size_t G = (size_t)sm_count * kMaxGridPerSm;
+  std::vector<unsigned long long> ws(kWsHeader / 8, 0ULL);
+  std::vector<double> part_loss(G, 0.0);
+  std::vector<long long> part_cnt(G, 0);
+  A.ntiles = sm_count;
+  std::vector<float> part_dT((size_t)A.ntiles * C * P.CKP, 0.f);
+  A.counter = &ws[WS_COUNTER];
+  A.part_loss = part_loss.data(); A.part_cnt = part_cnt.data(); A.part_dT = part_dT.data();
+  float grad_out = scale;
+  const long long n_dl = (long long)B * CK * h * w;
+  if (mode == MODE_STEP) {
+    A.grad_out = &grad_out;
+    A.count_local = reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]);
+    A.count_global = reinterpret_cast<double*>(&ws[WS_COUNT_GLOBAL]);
+    A.ws_hdr = ws.data();
+    PrepA pa{dlogits, n_dl, labels, (long long)B * H * W, C, ignore, label_bytes, ws.data()};
+    cpusimt::launch((unsigned)sm_count * 4, 256, prep_body, &pa);
+  } else if (mode != MODE_FWD) {
+    for (long long i = 0; i < n_dl; ++i) dlogits[i] = 0.f;     // cudaMemsetAsync
+  }
+  long long g = (long long)ctas_per_sm * sm_count;
+  const long long need = (A.nunits + P.NT / 32 - 1) / (P.NT / 32);
+  if (g > need) g = need;
+  if (g < 1) g = 1;
+  switch (mode) {
+    case MODE_FWD: rc = launch_any<MODE_FWD>(A, P, (unsigned)g, label_bytes); break;
+    case MODE_FWDBWD: rc = launch_any<MODE_FWDBWD>(A, P, (unsigned)g, label_bytes); break;
+    case MODE_BWD: rc = launch_any<MODE_BWD>(A, P, (unsigned)g, label_bytes); break;
+    case MODE_PLACE: rc = launch_any<MODE_PLACE>(A, P, (unsigned)g, 1); break;
+    case MODE_STEP: rc = launch_any<MODE_STEP>(A, P, (unsigned)g, label_bytes); break;
+    default: rc = SIMT_EINVAL;
+  }
+  if (rc) return rc;
+  FinA fa{part_dT.data(), part_loss.data(), part_cnt.data(), (int)g, mode == MODE_PLACE ? 0 : A.ntiles, CK, P.CKP, C,
+          mode == MODE_STEP ? MODE_STEP : mode, A.gscale, A.counter, stats, loss_mean, mode == MODE_PLACE ? nullptr : dT,
+          mode == MODE_PLACE ? nullptr : err, mode == MODE_STEP ? &grad_out : nullptr,
+          mode == MODE_STEP ? reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]) : nullptr, ws.data()};
+  const unsigned fgrid = mode == MODE_PLACE ? 1u : (unsigned)((C * P.CKP + 31) / 32 + 1);
+  cpusimt::launch(fgrid, 1024, fin_body, &fa);
+  // the invariants the next call relies on
+  if (ws[WS_COUNTER] != 0ULL) return -100;
+  for (float v : part_dT) if (v != 0.f) return -101;
+  return 0;
+}
+
+}  // extern "C"

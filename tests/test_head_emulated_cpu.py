@@ -1,0 +1,235 @@
+"""The fused head kernel ITSELF, executed on the CPU against the reference's golden vectors and the oracle (no GPU).
+
+csrc/head_kernel.cuh (all modes of the fused kernel), csrc/step_kernels.cuh (label-count prologue, finalize) and
+csrc/head_plan.cuh (launch plan) -- the files the product build compiles with nvcc -- are compiled with g++ against the
+CUDA-on-CPU shim of tests/cpu_simt (warps = 32 fibers, shuffles / votes / __syncwarp = barriers among them, random
+scheduling of lanes and warps, dynamic shared memory pre-filled with a NaN pattern) and driven through the launch
+sequences of csrc/head.cu (tests/cpu_simt/head_emul.cpp).  The inline-PTX helpers have host alternates behind
+SIMT_CPU_EMULATION: fma.rn.f32x2 -> two fmaf, ex2 / lg2 / rcp.approx -> libm, red.global.add -> add, %smid -> block index;
+everything else -- units, cells, label decoding, soft-max bounds, the transposed lerp, dT tiles, finalize -- is the
+product code.  Same bar as on the GPU: loss, dLogits, dT within 1e-5 (norm-wise and max-scaled) of the fp32 AND fp64
+reference (tests/golden, recorded from the unmodified reference)."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from util import HEAD_CASES, class_dist, load_golden, rel_l2, rel_max
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "build", "cpu_simt")
+TOL = 1e-5
+MODE_FWD, MODE_FWDBWD, MODE_BWD, MODE_PLACE, MODE_STEP = 0, 1, 2, 3, 4
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not found")
+
+
+def _build():
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libhead_emul.so")
+    csrc = os.path.join(ROOT, "simt_b200", "csrc")
+    deps = [os.path.join(ROOT, "tests", "cpu_simt", f) for f in ("head_emul.cpp", "cuda_shim.h")] + [
+        os.path.join(csrc, f) for f in ("common.cuh", "xchg.cuh", "step_xchg.cuh", "step_kernels.cuh", "head_kernel.cuh",
+                                        "head_plan.cuh", "stepx_acquire.inc", "stepx_cta0.inc")]
+    if os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(d) for d in deps):
+        return so
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas",
+           "-I", os.path.join(ROOT, "tests", "cpu_simt"), "-I", csrc, os.path.join(ROOT, "tests", "cpu_simt", "head_emul.cpp"),
+           "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return so
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = ctypes.CDLL(_build())
+    vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.emul_head.restype = i
+    lib.emul_head.argtypes = [i, vp, i, i, i, i, vp, i, vp, i, i, i, i, f, f, f, vp, vp, vp, vp, vp, i, i, i, i, ctypes.c_ulonglong]
+    return lib
+
+
+def run(lib, mode, logits, T, labels, size, i64=False, scale=1.0, seed=1, sm=3, cps=2, ur=0, rs=0, ignore=255,
+        thres=-1.0, lam=0.0, C=None):
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    B, CK, h, w = logits.shape
+    if C is None:
+        C = CK if T is None else T.shape[1]
+    Tc = None if T is None else np.ascontiguousarray(T, dtype=np.float32)
+    lab = None if labels is None else np.ascontiguousarray(np.asarray(labels).astype(np.int64 if i64 else np.uint8))
+    H, W = int(size[0]), int(size[1])
+    dl = np.full_like(logits, 7.0)                      # garbage: the call must zero / overwrite it
+    stats = np.full(2 + CK * C, -5.0, np.float64)
+    loss = np.full(1, -5.0, np.float32)
+    dT = np.full((CK, C), -5.0, np.float32)
+    err = np.zeros(1, np.int32)
+    rc = lib.emul_head(mode, logits.ctypes.data, B, CK, h, w, None if Tc is None else Tc.ctypes.data, C,
+                       None if lab is None else lab.ctypes.data, 8 if i64 else 1, H, W, ignore, scale, thres, lam,
+                       dl.ctypes.data, stats.ctypes.data, loss.ctypes.data, dT.ctypes.data, err.ctypes.data, sm, cps, ur, rs, seed)
+    assert rc == 0, f"emul_head returned {rc}"
+    return float(loss[0]), dl, dT, stats, int(err[0])
+
+
+def _check(got, ref, what):
+    assert rel_l2(got, ref) <= TOL, f"{what}: rel l2 {rel_l2(got, ref):.3e}"
+    assert rel_max(got, ref) <= TOL, f"{what}: rel max {rel_max(got, ref):.3e}"
+
+
+def _scaled(dl_raw, stats, shape_T, g=1.0):
+    """simt_head_scale: dlogits = raw * g / N, dT = raw dT * g / N"""
+    n = stats[1]
+    return dl_raw * (g / n), (stats[2:] * (g / n)).reshape(shape_T)
+
+
+@pytest.mark.parametrize("name", HEAD_CASES)
+@pytest.mark.parametrize("int64_labels", [False, True])
+def test_fused_kernel_vs_reference_golden(emu, name, int64_labels):
+    g = load_golden(name)
+    # simt_head_fwdbwd + simt_head_scale (the autograd entry)
+    loss, dl_raw, _, stats, err = run(emu, MODE_FWDBWD, g["logits"], g["T"], g["labels"], g["size"], int64_labels)
+    dl, dT = _scaled(dl_raw, stats, g["T"].shape)
+    assert err == 0
+    assert abs(loss - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    for ref in ("f32", "f64"):
+        _check(dl, g["dlogits_" + ref], "dlogits vs " + ref)
+        _check(dT, g["dT_" + ref], "dT vs " + ref)
+    # simt_head_step (HeadRunner.step): count pass, kernel applying grad_out / N itself, finalize
+    loss2, dl2, dT2, _, err = run(emu, MODE_STEP, g["logits"], g["T"], g["labels"], g["size"], int64_labels, scale=0.75, seed=2)
+    assert err == 0 and abs(loss2 - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _check(dl2, 0.75 * g["dlogits_f64"], "step dlogits")
+    _check(dT2, 0.75 * g["dT_f64"], "step dT")
+
+
+@pytest.mark.parametrize("name", ["head_small_r", "head_openset4", "head_openset15", "head_odd"])
+def test_forward_only_and_backward_with_host_scale(emu, name):
+    g = load_golden(name)
+    loss, _, _, stats, _ = run(emu, MODE_FWD, g["logits"], g["T"], g["labels"], g["size"])
+    assert abs(loss - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _, dl, dT, _, _ = run(emu, MODE_BWD, g["logits"], g["T"], g["labels"], g["size"], scale=float(0.5 / stats[1]), seed=3)
+    _check(dl, 0.5 * g["dlogits_f64"], "bwd dlogits")
+    _check(dT, 0.5 * g["dT_f64"], "bwd dT")
+
+
+@pytest.mark.parametrize("ur,rs", [(1, 0), (1, 1), (1, 2), (1, 4), (2, 0), (3, 0), (8, 0), (32, 0)])
+def test_unit_shapes_are_the_same_function(emu, ur, rs):
+    """every unit height (cell-rows per warp unit) and row split gives the same result"""
+    g = load_golden("head_cfg1_tile")
+    loss, dl_raw, _, stats, _ = run(emu, MODE_FWDBWD, g["logits"], g["T"], g["labels"], g["size"], ur=ur, rs=rs, seed=ur * 10 + rs)
+    dl, dT = _scaled(dl_raw, stats, g["T"].shape)
+    assert abs(loss - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _check(dl, g["dlogits_f32"], "dlogits")
+    _check(dT, g["dT_f32"], "dT")
+
+
+@pytest.mark.parametrize("sm,cps,seed", [(1, 1, 1), (2, 3, 2), (5, 2, 3), (7, 1, 4)])
+def test_grid_shapes_and_schedules(emu, sm, cps, seed):
+    """any number of SMs / resident CTAs and any interleaving of lanes and warps (dynamic unit claims, per-SM dT tiles)"""
+    g = load_golden("head_openset4")
+    loss, dl, dT, _, _ = run(emu, MODE_STEP, g["logits"], g["T"], g["labels"], g["size"], sm=sm, cps=cps, seed=seed)
+    assert abs(loss - float(g["loss_f32"])) <= TOL * abs(float(g["loss_f32"]))
+    _check(dl, g["dlogits_f64"], "dlogits")
+    _check(dT, g["dT_f64"], "dT")
+
+
+def test_plain_ce_T_none_and_huge_margins(emu):
+    """T = NULL (the IDENT instantiations): F.cross_entropy on the upsampled logits, finite where p_y underflows"""
+    from oracle import simt_oracle as O
+    logits, labels = O.synth_head_inputs(2, 19, 9, 17, 64, 128, seed=5, coherent=True, block=8)
+    for gap in (0.0, 60.0, 200.0, 1000.0):
+        x = logits * (0.5 if gap else 1.0)
+        if gap:
+            x = x.clone()
+            x[:, 3] += gap
+        lg = x.clone().requires_grad_(True)
+        ref = O.plain_ce_loss(lg, labels.long(), (64, 128))
+        ref.backward()
+        loss, dl, _, _, err = run(emu, MODE_STEP, x.numpy(), None, labels.numpy(), (64, 128), seed=int(gap) + 1)
+        assert err == 0 and np.isfinite(loss) and np.isfinite(dl).all(), gap
+        assert abs(loss - float(ref.detach())) <= TOL * abs(float(ref.detach())), gap
+        _check(dl, lg.grad.numpy(), f"dlogits, gap {gap}")
+
+
+def test_edge_cases(emu):
+    from oracle import simt_oracle as O
+    logits, labels = O.synth_head_inputs(1, 19, 5, 9, 32, 64, seed=9, coherent=True, block=8)
+    T = O.sig_ntm_forward(torch.randn(19, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, 0).numpy()
+    # every pixel ignored: mean over nothing = NaN, like the reference
+    loss, _, _, stats, err = run(emu, MODE_FWDBWD, logits.numpy(), T, np.full((1, 32, 64), 255), (32, 64))
+    assert np.isnan(loss) and stats[1] == 0 and err == 0
+    # a label in [C, 254]: error bit + NaN loss (the reference raises)
+    bad = labels.numpy().copy()
+    bad[0, 3, 5] = 77
+    loss, _, _, _, err = run(emu, MODE_FWDBWD, logits.numpy(), T, bad, (32, 64))
+    assert (err & 1) and np.isnan(loss)
+    # negative int64 labels are ignored (utils/loss.py:29), equal to marking them 255
+    neg = labels.numpy().astype(np.int64)
+    mask = neg == 255
+    neg[mask] = -3
+    a = run(emu, MODE_FWDBWD, logits.numpy(), T, neg, (32, 64), i64=True)
+    b = run(emu, MODE_FWDBWD, logits.numpy(), T, labels.numpy(), (32, 64))
+    assert a[3][1] == b[3][1] and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
+    # huge dynamic range inside a cell: rows fall back to the exact per-pixel maximum
+    big = logits.numpy() * 300.0
+    lo, dlo, dTo = O.simt_head_fwd_bwd(torch.from_numpy(big), torch.from_numpy(T), labels, (32, 64), torch.float64)
+    _, dl32, dT32 = O.simt_head_fwd_bwd(torch.from_numpy(big), torch.from_numpy(T), labels, (32, 64), torch.float32)
+    loss, dl, dT, _, _ = run(emu, MODE_STEP, big, T, labels.numpy(), (32, 64))
+    assert abs(loss - float(lo)) <= TOL * abs(float(lo))
+    # at |logit| ~ 1000 the fp32 lerp itself is only good to ~1e-4 in the exponent: the bar for the gradients is the
+    # fp32 reference's own distance from its fp64 self
+    assert np.isfinite(dl).all() and np.isfinite(dT).all()
+    assert rel_l2(dl, dlo.numpy()) <= max(TOL, 3 * rel_l2(dl32.numpy(), dlo.numpy()))
+    assert rel_l2(dT, dTo.numpy()) <= max(TOL, 3 * rel_l2(dT32.numpy(), dTo.numpy()))
+
+
+@pytest.mark.parametrize("name", ["place_K4", "place_K15", "place_K4_nothres"])
+def test_placeholder_mode_vs_reference_golden(emu, name):
+    """MODE_PLACE (Placeholder_loss, tools/trainV2_simt.py:202-230) against the reference's own function"""
+    g = load_golden(name)
+    K = int(g["K"])
+    loss, dl_raw, _, stats, _ = run(emu, MODE_PLACE, g["logits"], None, None, g["size"], thres=float(g["thres"]),
+                                    lam=float(g["lambda_place"]), C=19)
+    dl = dl_raw / stats[1]
+    assert g["logits"].shape[1] == 19 + K
+    assert abs(loss - float(g["loss_f64"])) <= TOL * abs(float(g["loss_f64"]))
+    assert rel_l2(dl, g["dlogits_f64"]) <= TOL
+    assert rel_max(dl, g["dlogits_f64"]) <= 5 * TOL
+
+
+def test_random_shapes_vs_oracle(emu):
+    """a short randomised sweep like tests/test_zfuzz_head_gpu.py: shapes, channel counts, label patterns, dtypes"""
+    from oracle import simt_oracle as O
+    rng = np.random.default_rng(3)
+    done = 0
+    while done < 12:
+        K = int(rng.choice([0, 4, 15, 1, 9]))
+        C, CK = 19, 19 + K
+        B = int(rng.integers(1, 3))
+        h, w = int(rng.integers(1, 12)), int(rng.integers(1, 14))
+        mode = rng.choice(["up", "up", "same", "down"])
+        if mode == "up":
+            H, W = h * int(rng.integers(1, 7)) + int(rng.integers(0, 5)), w * int(rng.integers(1, 7)) + int(rng.integers(0, 5))
+        elif mode == "same":
+            H, W = h, w
+        else:
+            H, W = max(1, h // 2), max(1, w // 2 + 1)
+        seed = int(rng.integers(0, 1 << 30))
+        lg, lab = O.synth_head_inputs(B, CK, h, w, H, W, seed=seed, coherent=bool(rng.integers(0, 2)),
+                                      ignore_frac=float(rng.choice([0.0, 0.1, 0.5])),
+                                      block=(int(rng.integers(1, 12)), int(rng.integers(1, 12))), logit_scale=float(rng.choice([0.5, 3.0, 12.0])))
+        if not bool(((lab >= 0) & (lab < C)).any()):
+            continue
+        T = O.sig_ntm_forward(torch.randn(CK, C, generator=torch.Generator().manual_seed(seed)), np.full(19, 1 / 19), C, K)
+        lo, dlo, dTo = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+        i64 = bool(rng.integers(0, 2))
+        loss, dl, dT, _, err = run(emu, MODE_STEP, lg.numpy(), T.numpy(), lab.numpy(), (H, W), i64=i64, seed=seed & 0xffff,
+                                   sm=int(rng.integers(1, 5)), cps=int(rng.integers(1, 4)))
+        tag = f"B={B} K={K} {h}x{w}->{H}x{W} int64={i64} seed={seed}"
+        assert err == 0, tag
+        assert abs(loss - float(lo)) <= TOL * abs(float(lo)), tag
+        assert rel_l2(dl, dlo.numpy()) <= TOL and rel_l2(dT, dTo.numpy()) <= TOL, tag
+        done += 1
