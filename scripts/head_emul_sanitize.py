@@ -22,7 +22,7 @@ def build():
     deps = [src, os.path.join(ROOT, "tests", "cpu_simt", "cuda_shim.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps):
         return
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fsanitize=address,undefined",
+    cmd = ["g++", "-O0", "-g", "-std=c++17", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fsanitize=address,undefined",
            "-fno-sanitize-recover=undefined", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests", "cpu_simt"), "-I", csrc,
            src, "-o", SO]
     print("building", SO, "(a few minutes)", flush=True)
@@ -64,6 +64,7 @@ def sweep(n_cases, seed):
         dl = np.empty_like(logits)
         stats = np.empty(2 + CK * C, np.float64); loss = np.empty(1, np.float32); dT = np.empty((CK, C), np.float32)
         err = np.zeros(1, np.int32)
+        if os.environ.get('HEAD_EMUL_VERBOSE'): print(case, dict(mode=mode,B=B,K=K,h=h,w=w,H=H,W=W,i64=i64,ident=ident,off=off), flush=True)
         rc = lib.emul_head(mode, logits.ctypes.data, B, CK, h, w, None if T is None else T.ctypes.data, C, lab.ctypes.data,
                            8 if i64 else 1, H, W, 255, 1.0, float(rng.choice([-1.0, 0.5])), 0.1, dl.ctypes.data, stats.ctypes.data,
                            loss.ctypes.data, dT.ctypes.data, err.ctypes.data, int(rng.integers(1, 5)), int(rng.integers(1, 4)),

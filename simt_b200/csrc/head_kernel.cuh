@@ -495,7 +495,12 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
           // exp-sum >= 2^(mlo - M): no pixel of this row can underflow the softmax denominator
           bool range_safe = (M - mlo) < 38.f;
           // plain CE: the label's own exponential must not underflow either (any real channel can be the label)
-          if (!PLACE && ident) range_safe = range_safe && (M + group_max<LPR>(-mall, 0xffffffffu)) < 60.f;
+          // (the shuffle inside group_max is a full-mask collective: it must be executed by every lane, so it may not
+          // sit behind `range_safe &&` -- lanes whose row already failed the first test would skip it)
+          if (!PLACE && ident) {
+            const float nmall = group_max<LPR>(-mall, 0xffffffffu);
+            range_safe = range_safe & ((M + nmall) < 60.f);
+          }
           const float2 nM = bcast2(-M);
 #pragma unroll
           for (int q = 0; q < NP; ++q) a[q] = fadd2(a[q], nM);

@@ -18,6 +18,7 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <cstdio>
 #include <random>
 #include <vector>
 
@@ -53,6 +54,7 @@ struct Fiber {
 
 struct Warp {
   unsigned long long buf[32];
+  const void* site[32];         // call site of the collective every lane is in (divergent collectives are reported)
   int arrived = 0;
   unsigned gen = 0;
 };
@@ -102,8 +104,13 @@ struct Rank {
 
 extern thread_local Rank* R;     // the emulator of the calling OS thread
 
+// debugging aid: when set (by a harness' SIGALRM handler) the next fiber that yields prints its backtrace and exits
+inline volatile int& debug_backtrace_flag() { static volatile int v = 0; return v; }
+void debug_backtrace_and_exit();   // harness
+
 inline void yield() {
   Rank* r = R;
+  if (debug_backtrace_flag()) debug_backtrace_and_exit();
   ++r->n_switch;
   swapcontext(&r->fibers[(size_t)r->cur].uc, &r->sched);
 }
@@ -195,11 +202,23 @@ inline int warp_width() {
   const unsigned left = r->bdim.x - w * 32;
   return (int)(left < 32 ? left : 32);
 }
-// all lanes of the warp (full mask: the emulated kernels only use 0xffffffff collectives in converged code)
-inline void warp_barrier() {
+// all lanes of the warp (full mask: the emulated kernels only use 0xffffffff collectives in converged code).
+// `site` != null: the first barrier of a collective -- every lane must have come from the SAME call site, otherwise the
+// kernel executes a full-mask collective in divergent code (undefined behaviour in CUDA) and the emulation stops.
+inline void warp_barrier(const void* site = nullptr) {
   const unsigned w = R->fibers[(size_t)R->cur].tid.x >> 5;
   const unsigned gen = R->warps[w].gen;
-  if (++R->warps[w].arrived == warp_width()) { R->warps[w].arrived = 0; ++R->warps[w].gen; return; }
+  if (site) R->warps[w].site[my_lane()] = site;
+  if (++R->warps[w].arrived == warp_width()) {
+    if (site)
+      for (int l = 1; l < warp_width(); ++l)
+        if (R->warps[w].site[l] != R->warps[w].site[0]) {
+          fprintf(stderr, "divergent warp collective: block %u warp %u lane 0 at %p, lane %d at %p\n", R->bid.x, w,
+                  R->warps[w].site[0], l, R->warps[w].site[l]);
+          die("lanes of one warp are in different full-mask collectives");
+        }
+    R->warps[w].arrived = 0; ++R->warps[w].gen; return;
+  }
   Fiber& f = R->fibers[(size_t)R->cur];
   f.wait_kind = 2; f.wait_gen = gen;
   while (R->warps[w].gen == gen) yield();
@@ -217,14 +236,15 @@ static inline void __syncthreads() { cpusimt::block_barrier(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __nanosleep(unsigned) { cpusimt::yield(); }
 
+#define SIMT_COLLECTIVE __attribute__((noinline)) static
 template <typename T>
-static inline T __shfl_xor_sync(unsigned, T v, int o) {
+SIMT_COLLECTIVE T __shfl_xor_sync(unsigned, T v, int o) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   const int lane = cpusimt::my_lane();
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = bits; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   { cpusimt::Warp& w = cpusimt::my_warp(); bits = w.buf[(lane ^ o) & 31]; }
   cpusimt::warp_barrier();
   T r;
@@ -232,12 +252,12 @@ static inline T __shfl_xor_sync(unsigned, T v, int o) {
   return r;
 }
 template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src) {
+SIMT_COLLECTIVE T __shfl_sync(unsigned, T v, int src) {
   const int lane = cpusimt::my_lane();
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = bits; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   { cpusimt::Warp& w = cpusimt::my_warp(); bits = w.buf[src & 31]; }
   cpusimt::warp_barrier();
   T r;
@@ -245,32 +265,32 @@ static inline T __shfl_sync(unsigned, T v, int src) {
   return r;
 }
 template <typename T>
-static inline T __shfl_up_sync(unsigned, T v, int delta) {
+SIMT_COLLECTIVE T __shfl_up_sync(unsigned, T v, int delta) {
   const int lane = cpusimt::my_lane();
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = bits; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   { cpusimt::Warp& w = cpusimt::my_warp(); bits = w.buf[lane >= delta ? lane - delta : lane]; }
   cpusimt::warp_barrier();
   T r;
   memcpy(&r, &bits, sizeof(T));
   return r;
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { cpusimt::warp_barrier(); }
-static inline bool __any_sync(unsigned, bool p) {
+SIMT_COLLECTIVE void __syncwarp(unsigned = 0xffffffffu) { cpusimt::warp_barrier(__builtin_return_address(0)); }
+SIMT_COLLECTIVE bool __any_sync(unsigned, bool p) {
   const int lane = cpusimt::my_lane();
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = p ? 1ULL : 0ULL; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   bool any = false;
   { cpusimt::Warp& w = cpusimt::my_warp(); for (int l = 0; l < cpusimt::warp_width(); ++l) any = any || (w.buf[l] != 0ULL); }
   cpusimt::warp_barrier();
   return any;
 }
-static inline int __reduce_max_sync(unsigned, int v) {
+SIMT_COLLECTIVE int __reduce_max_sync(unsigned, int v) {
   const int lane = cpusimt::my_lane();
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = (unsigned long long)(long long)v; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   int m = v;
   { cpusimt::Warp& w = cpusimt::my_warp(); for (int l = 0; l < cpusimt::warp_width(); ++l) { const int x = (int)(long long)w.buf[l]; m = x > m ? x : m; } }
   cpusimt::warp_barrier();
@@ -280,10 +300,10 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31u));
 }
 static inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one OS thread per rank
-static inline bool __all_sync(unsigned, bool p) {
+SIMT_COLLECTIVE bool __all_sync(unsigned, bool p) {
   const int lane = cpusimt::my_lane();
   { cpusimt::Warp& w = cpusimt::my_warp(); w.buf[lane] = p ? 1ULL : 0ULL; }
-  cpusimt::warp_barrier();
+  cpusimt::warp_barrier(__builtin_return_address(0));
   bool all = true;
   { cpusimt::Warp& w = cpusimt::my_warp(); for (int l = 0; l < cpusimt::warp_width(); ++l) all = all && (w.buf[l] != 0ULL); }
   cpusimt::warp_barrier();

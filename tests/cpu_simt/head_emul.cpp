@@ -27,6 +27,19 @@ thread_local Rank* R = nullptr;
 
 using namespace simt;
 
+// watchdog / debugging aid: when the alarm fires, the next fiber that yields prints its backtrace and the process exits
+#include <execinfo.h>
+#include <signal.h>
+static void on_alarm(int) { cpusimt::debug_backtrace_flag() = 1; }
+namespace cpusimt {
+void debug_backtrace_and_exit() {
+  void* bt[48];
+  const int n = backtrace(bt, 48);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(4);
+}
+}  // namespace cpusimt
+
 template <int CPL, int LPR, int MODE, typename L, int NT, int MINB, bool ID>
 static void kernel_body(void* p) { head_kernel<CPL, LPR, MODE, L, NT, MINB, ID>(*static_cast<const HeadArgs*>(p)); }
 
@@ -88,6 +101,14 @@ int emul_head(int mode, const float* logits, int B, int CK, int h, int w, const 
   cpusimt::Rank emu;
   emu.rng.seed(seed);
   cpusimt::R = &emu;
+  // watchdog: a kernel that spins (or lanes that livelock) ends the process with a backtrace instead of hanging the
+  // test run; HEAD_EMUL_ALARM=<seconds> overrides the 300 s default
+  {
+    const char* al = getenv("HEAD_EMUL_ALARM");
+    signal(SIGALRM, on_alarm);
+    alarm(al ? (unsigned)atoi(al) : 300u);
+  }
+  struct AlarmOff { ~AlarmOff() { alarm(0); } } alarm_off;
 
   HeadArgs A{};
   Plan P{};

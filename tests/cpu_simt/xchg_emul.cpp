@@ -35,6 +35,7 @@ thread_local Rank* R = nullptr;
   fflush(stderr);
   _exit(3);
 }
+void debug_backtrace_and_exit() { die("debug backtrace requested"); }
 }  // namespace cpusimt
 
 using namespace simt;

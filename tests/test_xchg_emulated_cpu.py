@@ -35,7 +35,7 @@ def _build(name, *defines):
         for f in ("xchg.cuh", "step_xchg.cuh", "step_kernels.cuh", "stepx_acquire.inc", "stepx_cta0.inc")]
     if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(d) for d in deps):
         return exe
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests", "cpu_simt"),
+    cmd = ["g++", "-O0", "-g", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests", "cpu_simt"),
            "-I", os.path.join(ROOT, "simt_b200", "csrc"), *defines, SRC, "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
