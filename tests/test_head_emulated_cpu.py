@@ -253,3 +253,76 @@ def test_random_shapes_vs_oracle(emu):
         assert abs(loss - float(lo)) <= TOL * abs(float(lo)), tag
         assert rel_l2(dl, dlo.numpy()) <= TOL and rel_l2(dT, dTo.numpy()) <= TOL, tag
         done += 1
+
+
+def test_the_gpu_fuzz_sweep_cases_on_the_emulator(emu):
+    """tests/test_zfuzz_head_gpu.py draws 120 random cases for the GPU; the same generator, the same cases and the same
+    1e-5 bar here, with the entry points replaced by the emulated kernel (simt_head -> fwdbwd + scale, HeadRunner.step ->
+    step, Placeholder_loss -> MODE_PLACE + scale)."""
+    import types
+
+    src = open(os.path.join(ROOT, "tests", "test_zfuzz_head_gpu.py")).read().replace('torch.device("cuda")', 'torch.device("cpu")')
+
+    class Leaf:
+        """stands in for a CUDA tensor that requires grad: .grad is filled by the fake loss' backward()"""
+        def __init__(self, t):
+            self.t, self.grad = t, None
+
+    class FakeLoss:
+        def __init__(self, value, grads):
+            self.value, self.grads = value, grads
+        def backward(self):
+            for leaf, g in self.grads:
+                if leaf is not None:
+                    leaf.grad = torch.from_numpy(np.ascontiguousarray(g))
+        def detach(self):
+            return self
+        def __float__(self):
+            return float(self.value)
+
+    def as_leaf(x):
+        return x if isinstance(x, Leaf) else Leaf(x)
+
+    def simt_head(x, T, lab, size):
+        x, Tl = as_leaf(x), (None if T is None else as_leaf(T))
+        Tn = None if Tl is None else Tl.t.detach().numpy()
+        loss, dl_raw, _, stats, err = run(emu, MODE_FWDBWD, x.t.detach().numpy(), Tn, lab.numpy(), size, seed=int(stats_seed[0]))
+        stats_seed[0] += 1
+        assert err == 0
+        dl = dl_raw / stats[1]
+        dT = None if Tn is None else (stats[2:] / stats[1]).reshape(Tn.shape).astype(np.float32)
+        return FakeLoss(loss, [(x, dl), (Tl, dT)])
+
+    class HeadRunner:
+        def __init__(self, B, CK, C, h, w, H, W, device=None, label_dtype=torch.uint8):
+            self.size, self.i64 = (H, W), label_dtype == torch.int64
+        def step(self, lg, T, lab):
+            loss, dl, dT, _, err = run(emu, MODE_STEP, lg.numpy(), None if T is None else T.numpy(), lab.numpy(), self.size,
+                                       i64=self.i64, seed=int(stats_seed[0]))
+            stats_seed[0] += 1
+            assert err == 0
+            return loss, torch.from_numpy(dl), torch.from_numpy(dT)
+
+    def Placeholder_loss(x, C, K, thres, out_size=None, lambda_place=0.1):
+        x = as_leaf(x)
+        loss, dl_raw, _, stats, _ = run(emu, MODE_PLACE, x.t.detach().numpy(), None, None, out_size,
+                                        thres=-1.0 if thres is None else float(thres), lam=float(lambda_place), C=C)
+        return FakeLoss(loss, [(x, dl_raw / stats[1])])
+
+    stats_seed = [1]
+    fake = types.SimpleNamespace(simt_head=simt_head, HeadRunner=HeadRunner, Placeholder_loss=Placeholder_loss,
+                                 check_errors=lambda dev=None: None)
+    # tensors "moved to the device" that ask for gradients become leaves of the fake autograd
+    orig_requires_grad_ = torch.Tensor.requires_grad_
+    g = {"__name__": "zfuzz_on_emulator", "__file__": os.path.join(ROOT, "tests", "test_zfuzz_head_gpu.py")}
+    try:
+        torch.Tensor.requires_grad_ = lambda self, flag=True: Leaf(self) if self.dtype == torch.float32 else orig_requires_grad_(self, flag)
+        import sys
+        sys.modules["simt_b200_fake_for_fuzz"] = fake
+        exec(compile(src.replace("import simt_b200  # noqa: E402", "import simt_b200_fake_for_fuzz as simt_b200"), "zfuzz_on_emulator", "exec"), g)
+        worst, fails = g["run_fuzz"](120, 0)
+    finally:
+        torch.Tensor.requires_grad_ = orig_requires_grad_
+        sys.modules.pop("simt_b200_fake_for_fuzz", None)
+    assert not fails, "\n".join(fails)
+    assert 0.0 < max(worst.values()) <= TOL and all(v > 0.0 for v in worst.values()), worst

@@ -49,7 +49,13 @@ def run_fuzz(n_cases, seed):
             continue
         T = O.sig_ntm_forward(torch.randn(CK, C, generator=torch.Generator().manual_seed(seed)), np.full(19, 1 / 19), C, K)
         entry = rng.choice(["autograd", "step", "step64", "place"])
-        tag = f"case {case}: {entry} B={B} K={K} {h}x{w}->{H}x{W} coh={coherent} ign={ign} scale={scale} seed={seed}"
+        # plain CE (T = None, the IDENT instantiations) on a share of the closed-set cases; a part of the rows is scaled
+        # down so that one warp holds range-safe and range-unsafe rows at once
+        plain = K == 0 and entry != "place" and bool(rng.integers(0, 3) == 0)
+        if plain:
+            lg = lg.clone()
+            lg[:, :, : max(1, h // 2)] *= 0.05
+        tag = f"case {case}: {entry} B={B} K={K} {h}x{w}->{H}x{W} coh={coherent} ign={ign} scale={scale} seed={seed} plain={plain}"
         try:
             if entry == "place":
                 thres = None if rng.integers(0, 2) else 0.5
@@ -68,18 +74,26 @@ def run_fuzz(n_cases, seed):
                     if max(e32.values()) <= TOL:
                         errs = e32
             else:
-                ref_l, ref_dl, ref_dT = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+                if plain:
+                    xr = lg.double().requires_grad_(True)
+                    ref_l = O.plain_ce_loss(xr, lab.long(), (H, W))
+                    ref_l.backward()
+                    ref_l, ref_dl, ref_dT = ref_l.detach(), xr.grad, None
+                else:
+                    ref_l, ref_dl, ref_dT = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+                Td = None if plain else T.to(dev)
                 if entry == "autograd":
-                    x, Tt = lg.to(dev).requires_grad_(True), T.to(dev).requires_grad_(True)
+                    x = lg.to(dev).requires_grad_(True)
+                    Tt = None if plain else Td.requires_grad_(True)
                     loss = simt_b200.simt_head(x, Tt, lab.to(torch.uint8).to(dev), (H, W))
                     loss.backward()
-                    dl, dT = x.grad, Tt.grad
+                    dl, dT = x.grad, (None if plain else Tt.grad)
                 else:
                     i64 = entry == "step64"
                     r = simt_b200.HeadRunner(B, CK, C, h, w, H, W, device=dev, label_dtype=torch.int64 if i64 else torch.uint8)
-                    loss, dl, dT = r.step(lg.to(dev), T.to(dev), (lab.long() if i64 else lab.to(torch.uint8)).to(dev))
+                    loss, dl, dT = r.step(lg.to(dev), Td, (lab.long() if i64 else lab.to(torch.uint8)).to(dev))
                 errs = {"loss": abs(float(loss) - float(ref_l)) / abs(float(ref_l)), "dl": rel_l2(dl.cpu().numpy(), ref_dl.numpy()),
-                        "dT": rel_l2(dT.cpu().numpy(), ref_dT.numpy())}
+                        "dT": 0.0 if plain else rel_l2(dT.cpu().numpy(), ref_dT.numpy())}
             simt_b200.check_errors(dev)
         except Exception as e:   # noqa: BLE001
             fails.append(f"{tag}: EXCEPTION {type(e).__name__}: {e}")
