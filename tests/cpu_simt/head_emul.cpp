@@ -8,8 +8,10 @@
 // (fma.rn.f32x2 -> two fmaf, ex2/lg2/rcp.approx -> libm, red.global.add -> add, %smid -> block index); warps are 32
 // fibers, shuffles / votes / __syncwarp are barriers among them and the scheduler picks fibers at random, so lanes and
 // warps make progress in arbitrary order; dynamic shared memory starts out as a NaN pattern.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <unistd.h>
 
 #define SIMT_CPU_EMULATION 1
@@ -164,6 +166,127 @@ int emul_head(int mode, const float* logits, int B, int CK, int h, int w, const 
   if (ws[WS_COUNTER] != 0ULL) return -100;
   for (float v : part_dT) if (v != 0.f) return -101;
   return 0;
+}
+
+// The sharded step end to end (simt_head_step_sharded / simt_head_finish_sharded, csrc/head.cu: run_step, and the host
+// logic of HeadRunner.step / finish): `world` ranks, one OS thread each, every rank runs `nsteps` steps on its shard of
+// the batch with the REAL fused kernel (MODE_STEPX) between the real prologue and finalize; peer stores are delayed and
+// reordered by the shim.  pipelined != 0: the next step's labels are announced and the all-reduce is deferred; finish()
+// after the last step.  Outputs are those of the last step, per rank.
+struct ShardedJob {
+  int world, nsteps, pipelined, Bper, CK, h, w, C, H, W, ignore, sm_count, cps;
+  const float* logits; const float* T; const uint8_t* labels; float grad_out;
+  float* dlogits; float* loss; float* dT; double* stats; int* err;
+  unsigned long long seed;
+  std::vector<unsigned char*> mail;
+  std::atomic<int> rc{0};
+};
+
+static void finish_body_x(void* p) {
+  struct A { unsigned long long* ws; XchgArgs X; FinishArgs F; };
+  A* a = static_cast<A*>(p);
+  head_finish_kernel(a->ws, a->X, a->F);
+}
+struct PrepX { float* dl; long long n_dl; const uint8_t* lab; const uint8_t* next; long long npix; int C, ignore; unsigned long long* ws; XchgArgs X; FinishArgs F; };
+static void prep_body_x(void* p) {
+  PrepX* a = static_cast<PrepX*>(p);
+  head_prep_kernel<uint8_t>(a->dl, a->n_dl, a->lab, a->next, a->npix, a->C, a->ignore, a->ws, a->X, a->F);
+}
+struct FinX { FinA f; XchgArgs X; int defer; };
+static void fin_body_x(void* p) {
+  FinX* a = static_cast<FinX*>(p);
+  head_finalize_kernel(a->f.part_dT, a->f.part_loss, a->f.part_cnt, a->f.nparts, a->f.ntiles, a->f.CK, a->f.CKP, a->f.C, a->f.mode, a->f.gscale,
+                       a->f.counter, a->f.stats, a->f.loss, a->f.dT, a->f.err, a->f.grad_out, a->f.count_dev, a->f.ws, a->X, a->defer);
+}
+
+static void sharded_rank(ShardedJob* J, int rank) {
+  cpusimt::Rank emu;
+  emu.rng.seed(J->seed * 977ULL + (unsigned long long)rank * 131ULL + 3ULL);
+  emu.p_deliver = 0.05 + 0.1 * (double)(emu.rng() % 8);
+  emu.p_flush_at_kernel_end = (emu.rng() % 2) ? 0.3 : 0.9;
+  cpusimt::R = &emu;
+  const int B = J->Bper, CK = J->CK, C = J->C, h = J->h, w = J->w, H = J->H, W = J->W;
+  const size_t nlog = (size_t)B * CK * h * w, nlab = (size_t)B * H * W;
+  const float* logits = J->logits + (size_t)rank * nlog;
+  const uint8_t* labels = J->labels + (size_t)rank * nlab;
+  float* dlogits = J->dlogits + (size_t)rank * nlog;
+  double* stats = J->stats + (size_t)rank * (2 + CK * C);
+  float* dT = J->dT + (size_t)rank * CK * C;
+  float* loss = J->loss + rank;
+  int* err = J->err + rank;
+  float grad_out = J->grad_out;
+
+  XchgArgs X{};
+  for (int r = 0; r < J->world; ++r) X.mail[r] = J->mail[(size_t)r];
+  X.rank = rank; X.world = J->world; X.n_stats = 2 + CK * C; X.slot_entries = 2 + C * kXchgMaxCKP; X.max_spins = 0;
+
+  HeadArgs A{};
+  Plan P{};
+  A.logits = logits; A.T = J->T; A.labels = labels;
+  A.B = B; A.CK = CK; A.C = C; A.h = h; A.w = w; A.H = H; A.W = W; A.ignore = J->ignore;
+  A.gscale = 1.f; A.dlogits = dlogits; A.err = err; A.grad_out = &grad_out; A.X = X;
+  A.label_words_ok = ((reinterpret_cast<uintptr_t>(labels) & 3) == 0 && ((nlab & 3) == 0)) ? 1 : 0;
+  if (make_plan_for(MODE_STEP, B, CK, C, h, w, H, W, PlanTuning{0, 0, 0}, J->sm_count, &A, &P)) { J->rc = -1; return; }
+  const size_t G = (size_t)J->sm_count * kMaxGridPerSm;
+  std::vector<unsigned long long> ws(kWsHeader / 8 + (size_t)(2 + CK * C) + 16, 0ULL);
+  std::vector<double> part_loss(G, 0.0);
+  std::vector<long long> part_cnt(G, 0);
+  A.ntiles = J->sm_count;
+  std::vector<float> part_dT((size_t)A.ntiles * C * P.CKP, 0.f);
+  A.counter = &ws[WS_COUNTER];
+  A.count_local = reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]);
+  A.count_global = reinterpret_cast<double*>(&ws[WS_COUNT_GLOBAL]);
+  A.ws_hdr = ws.data();
+  A.part_loss = part_loss.data(); A.part_cnt = part_cnt.data(); A.part_dT = part_dT.data();
+  FinishArgs F{stats, loss, dT, &grad_out, err, CK, C, P.CKP};
+  A.fin = F;
+  long long g = (long long)J->cps * J->sm_count;
+  const long long need = (A.nunits + P.NT / 32 - 1) / (P.NT / 32);
+  if (g > need) g = need;
+  if (g < 1) g = 1;
+
+  bool deferred = false;
+  auto finish = [&]() {
+    struct { unsigned long long* ws; XchgArgs X; FinishArgs F; } a{ws.data(), X, F};
+    cpusimt::launch((unsigned)((X.n_stats + 255) / 256), 256, finish_body_x, &a);
+    deferred = false;
+  };
+  for (int s = 1; s <= J->nsteps; ++s) {
+    usleep((useconds_t)(emu.rng() % 300));
+    const bool defer = J->pipelined != 0;
+    const bool announce = defer && s < J->nsteps;
+    if (!defer && deferred) finish();
+    deferred = defer;
+    PrepX pa{dlogits, (long long)nlog, labels, announce ? labels : nullptr, (long long)nlab, C, J->ignore, ws.data(), X, F};
+    cpusimt::launch((unsigned)J->sm_count * 4, 256, prep_body_x, &pa);
+    if (launch_mode<MODE_STEPX, uint8_t, false>(A, P, (unsigned)g)) { J->rc = -2; return; }
+    FinX fa{FinA{part_dT.data(), part_loss.data(), part_cnt.data(), (int)g, A.ntiles, CK, P.CKP, C, MODE_STEP, 1.f, A.counter, stats, loss, dT,
+                 err, &grad_out, reinterpret_cast<double*>(&ws[WS_COUNT_LOCAL]), ws.data()}, X, defer ? 1 : 0};
+    cpusimt::launch((unsigned)((C * P.CKP + 31) / 32 + 1), 1024, fin_body_x, &fa);
+  }
+  finish();
+  emu.flush();
+}
+
+int emul_head_sharded(int world, int nsteps, int pipelined, const float* logits, int Bper, int CK, int h, int w, const float* T,
+                      int C, const uint8_t* labels, int H, int W, int ignore, float grad_out, float* dlogits, float* loss, float* dT,
+                      double* stats, int* err, int sm_count, int cps, unsigned long long seed) {
+  if (world < 2 || world > kMaxPeers || !logits || !T || !labels || nsteps < 1) return SIMT_EINVAL;
+  ShardedJob J;
+  J.world = world; J.nsteps = nsteps; J.pipelined = pipelined; J.Bper = Bper; J.CK = CK; J.h = h; J.w = w; J.C = C; J.H = H; J.W = W;
+  J.ignore = ignore; J.sm_count = sm_count; J.cps = cps; J.logits = logits; J.T = T; J.labels = labels; J.grad_out = grad_out;
+  J.dlogits = dlogits; J.loss = loss; J.dT = dT; J.stats = stats; J.err = err; J.seed = seed;
+  const size_t slot = 2 + (size_t)C * kXchgMaxCKP;
+  const size_t bytes = kHdrBytes + kCountBytes + (size_t)2 * kMaxPeers * (2 * slot) * sizeof(unsigned long long);
+  for (int r = 0; r < world; ++r) J.mail.push_back(static_cast<unsigned char*>(calloc(bytes, 1)));
+  signal(SIGALRM, on_alarm);
+  alarm(300u);
+  std::vector<std::thread> th;
+  for (int r = 0; r < world; ++r) th.emplace_back(sharded_rank, &J, r);
+  for (auto& t : th) t.join();
+  alarm(0);
+  for (unsigned char* m : J.mail) free(m);
+  return J.rc.load();
 }
 
 }  // extern "C"

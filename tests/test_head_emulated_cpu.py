@@ -326,3 +326,37 @@ def test_the_gpu_fuzz_sweep_cases_on_the_emulator(emu):
         sys.modules.pop("simt_b200_fake_for_fuzz", None)
     assert not fails, "\n".join(fails)
     assert 0.0 < max(worst.values()) <= TOL and all(v > 0.0 for v in worst.values()), worst
+
+
+@pytest.mark.parametrize("world,pipelined,K", [(2, 0, 0), (2, 1, 0), (4, 0, 4), (4, 1, 4), (8, 1, 0)])
+def test_sharded_step_end_to_end_equals_the_global_batch(emu, world, pipelined, K):
+    """simt_head_step_sharded on `world` emulated ranks (real prologue, REAL fused kernel in its MODE_STEPX
+    instantiation, real finalize / finish; peer stores delayed and reordered) against the reference semantics: the
+    single process sees the whole batch (tools/trainV2_simt.py:408-409,428) -- loss and dT of every rank equal the
+    global-batch answer, dLogits of a rank equal its slice of it, and the all-reduced stats are bitwise identical on
+    all ranks."""
+    from oracle import simt_oracle as O
+    vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    emu.emul_head_sharded.restype = i
+    emu.emul_head_sharded.argtypes = [i, i, i, vp, i, i, i, i, vp, i, vp, i, i, i, f, vp, vp, vp, vp, vp, i, i, ctypes.c_ulonglong]
+    C, CK, h, w, H, W, Bper, g = 19, 19 + K, 5, 9, 32, 64, 1, 0.75
+    logits, labels = O.synth_head_inputs(world * Bper, CK, h, w, H, W, seed=300 + world, coherent=True, block=(6, 10), ignore_frac=0.2)
+    T = O.sig_ntm_forward(torch.randn(CK, C, generator=torch.Generator().manual_seed(world)), class_dist(), C, K)
+    lo, dlo, dTo = O.simt_head_fwd_bwd(logits, T, labels, (H, W), torch.float64)
+    lg = np.ascontiguousarray(logits.numpy(), dtype=np.float32)
+    lab = np.ascontiguousarray(labels.numpy().astype(np.uint8))
+    Tn = np.ascontiguousarray(T.numpy(), dtype=np.float32)
+    dl = np.full_like(lg, 7.0)
+    loss = np.zeros(world, np.float32)
+    dT = np.zeros((world, CK, C), np.float32)
+    stats = np.zeros((world, 2 + CK * C), np.float64)
+    err = np.zeros(world, np.int32)
+    rc = emu.emul_head_sharded(world, 4, pipelined, lg.ctypes.data, Bper, CK, h, w, Tn.ctypes.data, C, lab.ctypes.data, H, W, 255, g,
+                               dl.ctypes.data, loss.ctypes.data, dT.ctypes.data, stats.ctypes.data, err.ctypes.data, 2, 2, 11 + world)
+    assert rc == 0 and not err.any()
+    for r in range(world):
+        assert abs(float(loss[r]) - float(lo)) <= TOL * abs(float(lo)), r
+        _check(dT[r], g * dTo.numpy(), f"dT of rank {r}")
+        _check(dl[r * Bper:(r + 1) * Bper], g * dlo.numpy()[r * Bper:(r + 1) * Bper], f"dlogits of rank {r}")
+        assert stats[r].tobytes() == stats[0].tobytes(), r
+        assert loss[r].tobytes() == loss[0].tobytes() and dT[r].tobytes() == dT[0].tobytes(), r
