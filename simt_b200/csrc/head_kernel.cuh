@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(NT, MINB) head_kernel(const HeadArgs A) {
   const LabelT* labels = reinterpret_cast<const LabelT*>(A.labels);
   const LabelT* labels_end = labels + (long long)A.B * A.H * A.W;
   const int h = A.h, w = A.w;
-  const int ign8 = (A.ignore >= 0 && A.ignore <= 255) ? A.ignore : 256;
+  // the byte code that means "ignored".  An ignore label outside 0..255 matches no uint8 label (256); int64 labels are
+  // converted by LabelFetch<long long>::one, which emits 0xFF for ignored / negative labels in that case
+  const int ign8 = (A.ignore >= 0 && A.ignore <= 255) ? A.ignore : (sizeof(LabelT) == 8 ? 255 : 256);
   // plain CE (T = NULL -> I): q = p_y can underflow where torch's log_softmax stays finite; its own instantiation, so
   // that the T-corrected kernels carry none of the extra range tracking
   constexpr bool ident = IDENT;

@@ -360,3 +360,28 @@ def test_sharded_step_end_to_end_equals_the_global_batch(emu, world, pipelined, 
         _check(dl[r * Bper:(r + 1) * Bper], g * dlo.numpy()[r * Bper:(r + 1) * Bper], f"dlogits of rank {r}")
         assert stats[r].tobytes() == stats[0].tobytes(), r
         assert loss[r].tobytes() == loss[0].tobytes() and dT[r].tobytes() == dT[0].tobytes(), r
+
+
+def test_ignore_labels_outside_the_byte_range(emu):
+    """Regression (found with this emulation): with an ignore label outside 0..255 (e.g. -1), int64 labels that are
+    negative or equal to it were converted to the byte code 0xFF, which the kernel then did NOT treat as 'ignored' ->
+    a false LABEL_RANGE error and a NaN loss.  The reference ignores `target < 0` and `target == ignore_label`
+    whatever the value (utils/loss.py:29-30)."""
+    from oracle import simt_oracle as O
+    logits, labels = O.synth_head_inputs(2, 19, 5, 9, 32, 64, seed=9, coherent=True, block=8, ignore_frac=0.0)
+    T = O.sig_ntm_forward(torch.randn(19, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, 0)
+    for ign in (-1, 300, -100):
+        lab = labels.clone().long()
+        lab[0, :5] = ign
+        lab[1, 7, 3:40] = -7                      # negative labels are ignored whatever the ignore label is
+        lo, dlo, dTo = O.simt_head_fwd_bwd(logits, T, lab, (32, 64), torch.float64, ignore_label=ign)
+        loss, dl, dT, _, err = run(emu, MODE_STEP, logits.numpy(), T.numpy(), lab.numpy(), (32, 64), i64=True, ignore=ign, seed=3)
+        assert err == 0, ign
+        assert abs(loss - float(lo)) <= TOL * abs(float(lo)), ign
+        _check(dl, dlo.numpy(), f"dlogits, ignore {ign}")
+        _check(dT, dTo.numpy(), f"dT, ignore {ign}")
+    # uint8 labels: an ignore label outside the byte range matches nothing, so a raw 255 is a contract violation
+    lab8 = labels.clone()
+    lab8[0, 0, 0] = 255
+    loss, _, _, _, err = run(emu, MODE_STEP, logits.numpy(), T.numpy(), lab8.numpy(), (32, 64), ignore=300, seed=4)
+    assert (err & 1) and np.isnan(loss)
