@@ -385,3 +385,38 @@ def test_ignore_labels_outside_the_byte_range(emu):
     lab8[0, 0, 0] = 255
     loss, _, _, _, err = run(emu, MODE_STEP, logits.numpy(), T.numpy(), lab8.numpy(), (32, 64), ignore=300, seed=4)
     assert (err & 1) and np.isnan(loss)
+
+
+@pytest.mark.parametrize("h,w,H,W,K,i64,coherent", [
+    (2, 3, 50, 90, 0, False, False), (2, 3, 50, 90, 4, True, False), (2, 2, 33, 129, 15, False, False),
+    (1, 2, 7, 300, 0, True, False), (2, 5, 3, 100, 0, False, False)])
+def test_runs_longer_than_the_prefetched_labels(emu, h, w, H, W, K, i64, coherent):
+    """large up-sampling factors: a cell's pixel run exceeds the 8 labels that travel in one word, so labels are fetched
+    one by one (both walking directions of the boustrophedon rows)"""
+    from oracle import simt_oracle as O
+    CK = 19 + K
+    lg, lab = O.synth_head_inputs(1, CK, h, w, H, W, seed=h * 100 + W, coherent=coherent, ignore_frac=0.1, block=(3, 5))
+    T = O.sig_ntm_forward(torch.randn(CK, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, K)
+    lo, dlo, dTo = O.simt_head_fwd_bwd(lg, T, lab, (H, W), torch.float64)
+    loss, dl, dT, _, err = run(emu, MODE_STEP, lg.numpy(), T.numpy(), lab.numpy(), (H, W), i64=i64, seed=3)
+    assert err == 0 and abs(loss - float(lo)) <= TOL * abs(float(lo))
+    _check(dl, dlo.numpy(), "dlogits")
+    _check(dT, dTo.numpy(), "dT")
+
+
+def test_upstream_gradient_values_and_an_all_ignored_image(emu):
+    from oracle import simt_oracle as O
+    lg, lab = O.synth_head_inputs(3, 19, 5, 9, 32, 64, seed=21, coherent=True, block=8, ignore_frac=0.1)
+    lab = lab.clone()
+    lab[1] = 255                                   # one image of the batch has no valid pixel at all
+    T = O.sig_ntm_forward(torch.randn(19, 19, generator=torch.Generator().manual_seed(4)), class_dist(), 19, 0)
+    lo, dlo, dTo = O.simt_head_fwd_bwd(lg, T, lab, (32, 64), torch.float64)
+    for g in (1.0, -2.5, 0.0, 1e-8, 3e4):
+        loss, dl, dT, _, err = run(emu, MODE_STEP, lg.numpy(), T.numpy(), lab.numpy(), (32, 64), scale=g, seed=5)
+        assert err == 0 and abs(loss - float(lo)) <= TOL * abs(float(lo))
+        assert not dl[1].any()                      # the all-ignored image receives exactly zero gradient
+        if g == 0.0:
+            assert not dl.any() and not dT.any()
+        else:
+            _check(dl, g * dlo.numpy(), f"dlogits, grad_out {g}")
+            _check(dT, g * dTo.numpy(), f"dT, grad_out {g}")
