@@ -45,7 +45,7 @@ void debug_backtrace_and_exit() {
 template <int CPL, int LPR, int MODE, typename L, int NT, int MINB, bool ID>
 static void kernel_body(void* p) { head_kernel<CPL, LPR, MODE, L, NT, MINB, ID>(*static_cast<const HeadArgs*>(p)); }
 
-// the instantiations the tests use: (10,2) for CK <= 20, (12,2) for CK <= 24, (10,4) for CK <= 40
+// the instantiations the tests use: (10,2) for CK <= 20, (12,2) for CK <= 24, (10,4) for CK <= 40, (16,4) for CK <= 64
 template <int MODE, typename L, bool ID>
 static int launch_mode(const HeadArgs& A, const Plan& P, unsigned grid) {
   void (*body)(void*) = nullptr;
@@ -53,6 +53,7 @@ static int launch_mode(const HeadArgs& A, const Plan& P, unsigned grid) {
 #ifndef HEAD_EMUL_SMALL
   if (P.CPL == 12 && P.LPR == 2) body = kernel_body<12, 2, MODE, L, 128, 2, ID>;
   if (P.CPL == 10 && P.LPR == 4) body = kernel_body<10, 4, MODE, L, 128, 3, ID>;
+  if (P.CPL == 16 && P.LPR == 4) body = kernel_body<16, 4, MODE, L, 128, 2, ID>;
 #endif
   if (!body) return SIMT_EUNSUPPORTED;
   HeadArgs a = A;

@@ -420,3 +420,24 @@ def test_upstream_gradient_values_and_an_all_ignored_image(emu):
         else:
             _check(dl, g * dlo.numpy(), f"dlogits, grad_out {g}")
             _check(dT, g * dTo.numpy(), f"dT, grad_out {g}")
+
+
+@pytest.mark.parametrize("CK,C", [(41, 19), (64, 19), (64, 64)])
+def test_widest_instantiation_up_to_64_channels(emu, CK, C):
+    """(CPL, LPR) = (16, 4) serves 41..64 channels -- more than any configuration of the reference uses (K <= 15);
+    covered here so that the instantiation the library ships is one that has run"""
+    from oracle import simt_oracle as O
+    K = CK - C
+    lg, lab = O.synth_head_inputs(1, CK, 5, 9, 32, 64, seed=CK, coherent=True, ignore_frac=0.1, block=(6, 10))
+    if C != 19:
+        lab = torch.from_numpy(np.random.default_rng(CK).integers(0, C, size=tuple(lab.shape))).to(lab.dtype)
+    Tm = torch.softmax(torch.randn(CK, C, generator=torch.Generator().manual_seed(4)), 1)
+    lo, dlo, dTo = O.simt_head_fwd_bwd(lg, Tm, lab, (32, 64), torch.float64)
+    loss, dl, dT, _, err = run(emu, MODE_STEP, lg.numpy(), Tm.numpy(), lab.numpy(), (32, 64), seed=3)
+    assert err == 0 and abs(loss - float(lo)) <= TOL * abs(float(lo))
+    _check(dl, dlo.numpy(), "dlogits")
+    _check(dT, dTo.numpy(), "dT")
+    rl, rdl = O.placeholder_fwd_bwd(lg, (32, 64), C, K, 0.3, 0.1, torch.float64)
+    loss, dl_raw, _, stats, _ = run(emu, MODE_PLACE, lg.numpy(), None, None, (32, 64), thres=0.3, lam=0.1, C=C)
+    assert abs(loss - float(rl)) <= TOL * abs(float(rl))
+    assert rel_l2(dl_raw / stats[1], rdl.numpy()) <= TOL
