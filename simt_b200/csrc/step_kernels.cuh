@@ -240,34 +240,38 @@ __global__ void __launch_bounds__(1024) head_finalize_kernel(
     const int y = o / CKP, k = o - y * CKP;
     const bool mine = o < ndt && k < CK;
     const int i = 2 + k * C + y;     // index in the caller's stats buffer; the slot keeps the tile order (entry 2 + o)
-    if (mine && ty < X.world && !defer)
+    // warp r (ty = r < world) handles rank r: it pushes this block's entries into rank r's mailbox and collects rank
+    // r's entries from this rank's own mailbox, so the `world` polls run concurrently in different warps (one after
+    // the other they cost ~0.7 us per system-scope load and rank)
+    if (mine && ty < X.world && !defer) {
       ll_push_f64(slot_of(X.mail[ty], par, X.rank, X.slot_entries), 2 + o, seq, sm[0][tx]);   // (not stats[i]: warp 0 overwrites it)
+      double v = 0.0;
+      if (!ll_wait_f64(slot_of(own, par, ty, X.slot_entries), 2 + o, seq, X.max_spins, &v)) s_bad = 1;
+      sm[1 + ty][tx] = v;
+    }
+    __syncthreads();
     if (mine && ty == 0 && !defer) {
       double t = 0.0;
-      bool ok = true;
-      for (int r = 0; r < X.world; ++r) {
-        double v = 0.0;
-        ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), 2 + o, seq, X.max_spins, &v) && ok;
-        t += v;
-      }
-      if (!ok) s_bad = 1;
+      for (int r = 0; r < X.world; ++r) t += sm[1 + r][tx];   // rank order: bitwise identical on every rank
+      const bool ok = s_bad == 0;
       stats[i] = ok ? t : (double)poison;
       if (dT_out) dT_out[i - 2] = ok ? (float)(t * sc) : poison;
     }
   } else {
-    if (tid < 2 * X.world && !defer)
-      ll_push_f64(slot_of(X.mail[tid >> 1], par, X.rank, X.slot_entries), tid & 1, seq, stats[tid & 1]);
+    // {loss sum, valid count}: thread 2 r + e handles entry e of rank r
+    if (tid < 2 * X.world && !defer) {
+      const int e = tid & 1, r = tid >> 1;
+      ll_push_f64(slot_of(X.mail[r], par, X.rank, X.slot_entries), e, seq, stats[e]);
+      double v = 0.0;
+      if (!ll_wait_f64(slot_of(own, par, r, X.slot_entries), e, seq, X.max_spins, &v)) s_bad = 1;
+      sm[1 + r][e] = v;
+    }
     __syncthreads();
     if (tid == 0 && !defer) {
       double t[2] = {0.0, 0.0};
-      bool ok = true;
-      for (int i = 0; i < 2; ++i)
-        for (int r = 0; r < X.world; ++r) {
-          double v = 0.0;
-          ok = ll_wait_f64(slot_of(own, par, r, X.slot_entries), i, seq, X.max_spins, &v) && ok;
-          t[i] += v;
-        }
-      if (!ok) s_bad = 1;
+      for (int e = 0; e < 2; ++e)
+        for (int r = 0; r < X.world; ++r) t[e] += sm[1 + r][e];
+      const bool ok = s_bad == 0;
       stats[0] = ok ? t[0] : (double)poison;
       stats[1] = ok ? t[1] : (double)poison;
       if (loss_mean) {
