@@ -17,6 +17,15 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a kernel that never returns must not hold the GPU box until the outer limit: pytest-timeout's "thread" method
+        # ends the process (and with it the CUDA context) even when the main thread is blocked inside the driver
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(1500, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
