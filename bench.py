@@ -789,6 +789,22 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def arm_watchdog(seconds):
+    """A kernel that never returns must not hold the GPU box until the driver's limit: end the process (and its CUDA
+    context) from a timer thread.  SIMT_BENCH_WATCHDOG_S overrides; 0 disables."""
+    seconds = float(os.environ.get("SIMT_BENCH_WATCHDOG_S", seconds))
+    if seconds <= 0:
+        return
+
+    def fire():
+        sys.stderr.write(f"bench.py: watchdog after {seconds:.0f} s -- giving up (a hung kernel or collective)\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -814,6 +830,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         sys.exit(subprocess.call(cmd))
+    arm_watchdog(800)
     run_ours(args, rank, local_rank, world)
 
 
